@@ -1,0 +1,24 @@
+"""kvpress_b200 — the score -> top-k -> gather hot path of NVIDIA/kvpress as hand-written sm_100a
+CUDA behind the reference's own press API (BasePress / ScorerPress hooks and the
+"kv-press-text-generation" pipeline). See DESIGN.md for scope and INTEGRATION.md for the C ABI.
+"""
+from kvpress_b200.pipeline import KVPressTextGenerationPipeline
+from kvpress_b200.presses.base_press import SUPPORTED_MODELS, BasePress
+from kvpress_b200.presses.decoding_press import DecodingPress
+from kvpress_b200.presses.expected_attention_press import ExpectedAttentionPress
+from kvpress_b200.presses.knorm_press import KnormPress
+from kvpress_b200.presses.scorer_press import ScorerPress
+from kvpress_b200.presses.snapkv_press import SnapKVPress
+from kvpress_b200.presses.streaming_llm_press import StreamingLLMPress
+
+__all__ = [
+    "BasePress",
+    "ScorerPress",
+    "KnormPress",
+    "SnapKVPress",
+    "ExpectedAttentionPress",
+    "StreamingLLMPress",
+    "DecodingPress",
+    "KVPressTextGenerationPipeline",
+    "SUPPORTED_MODELS",
+]

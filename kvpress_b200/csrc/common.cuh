@@ -1,0 +1,234 @@
+// common.cuh — shared device helpers and the internal (C++) launcher interface.
+// sm_100a only. No torch types anywhere in csrc/.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/kvpress_b200.h"
+
+namespace kvp {
+
+// ---- tiling of the sequence axis for the select / compact stages --------------------------
+constexpr int kTile = 1024;         // positions per tile (one CTA of kTileThreads)
+constexpr int kTileThreads = 256;   // 4 positions per thread
+constexpr int kSfxStride = 264;     // u16 per tile record: sfx[0..256], gt_hi at [257], padding
+constexpr uint16_t kForcedKey = 0xFFFFu;  // ordered key of a forced-keep position
+
+struct Strides3 {
+    int64_t b, h, s;
+};
+
+// Device view of the scratch area (carved by carve_workspace in api.cu).
+struct Workspace {
+    uint16_t* keys;      // [R][S_pad] ordered 16-bit keys of the scores
+    uint32_t* hist_hi;   // [R][256]   histogram of key >> 8
+    uint32_t* hist_lo;   // [R][256]   histogram of key & 255 among keys with hi == threshold bin
+    uint16_t* tile_sfx;  // [R][n_tiles][kSfxStride]
+    void* scorer;        // scorer-specific scratch (SnapKV / ExpectedAttention)
+    size_t scorer_bytes;
+    int S_pad;
+    int n_tiles;
+};
+
+struct Dims {
+    int B, H, Hq, S, D, n_kept;
+    int R;  // B * H rows
+    Strides3 ks, vs;
+};
+
+// ---- 16-bit float -> ordered unsigned key (same for bf16 and fp16: sign-magnitude) --------
+__host__ __device__ __forceinline__ uint16_t ordered_key16(uint16_t bits) {
+    if (bits == 0x8000u) bits = 0;  // -0 == +0 (torch.topk compares by value)
+    return (bits & 0x8000u) ? (uint16_t)(~bits) : (uint16_t)(bits | 0x8000u);
+}
+__host__ __device__ __forceinline__ uint16_t key16_to_bits(uint16_t key) {
+    return (key & 0x8000u) ? (uint16_t)(key & 0x7FFFu) : (uint16_t)(~key);
+}
+
+template <typename T>
+struct F16Traits;
+template <>
+struct F16Traits<__nv_bfloat16> {
+    static __device__ __forceinline__ float2 unpack2(uint32_t w) {
+        return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+    }
+    static __device__ __forceinline__ uint16_t from_float(float f) {
+        return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+    }
+    static __device__ __forceinline__ float to_float(uint16_t b) {
+        return __uint_as_float(((uint32_t)b) << 16);
+    }
+};
+template <>
+struct F16Traits<__half> {
+    static __device__ __forceinline__ float2 unpack2(uint32_t w) {
+        __half2 h = *reinterpret_cast<__half2*>(&w);
+        return __half22float2(h);
+    }
+    static __device__ __forceinline__ uint16_t from_float(float f) {
+        return __half_as_ushort(__float2half_rn(f));
+    }
+    static __device__ __forceinline__ float to_float(uint16_t b) {
+        return __half2float(__ushort_as_half(b));
+    }
+};
+
+// ---- cache-hinted 128-bit global accesses ---------------------------------------------------
+// sm_100a only accepts the bare .L2::evict_* qualifiers on 256-bit accesses; 128-bit accesses take
+// an explicit createpolicy handle through .L2::cache_hint.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int4 ldg_hint(const void* p, uint64_t pol) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ int4 ldg_plain(const void* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_hint(void* p, const int4& v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+}
+
+// ---- 256-bin suffix search, executed by ONE full warp ----------------------------------------
+// Finds the largest bin b with sum_{i>=b} hist[i] >= need (need >= 1) and returns
+// above = sum_{i>b} hist[i]. hist lives in shared memory. All 32 lanes get the result.
+__device__ __forceinline__ void warp_suffix_find(const uint32_t* hist, uint32_t need, int lane,
+                                                 int& bin, uint32_t& above) {
+    const int top = 255 - 8 * lane;  // this lane owns bins top, top-1, ..., top-7
+    uint32_t h[8];
+    uint32_t lane_sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        h[i] = hist[top - i];
+        lane_sum += h[i];
+    }
+    uint32_t incl = lane_sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    const unsigned crossed = __ballot_sync(0xFFFFFFFFu, incl >= need);
+    int my_bin = 0;
+    uint32_t my_above = 0;
+    const int first = crossed ? (__ffs(crossed) - 1) : 31;
+    if (lane == first) {
+        uint32_t run = incl - lane_sum;
+        my_bin = top - 7;
+        my_above = incl - h[7];
+        bool found = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (!found && run + h[i] >= need) {
+                my_bin = top - i;
+                my_above = run;
+                found = true;
+            }
+            run += h[i];
+        }
+    }
+    bin = __shfl_sync(0xFFFFFFFFu, my_bin, first);
+    above = __shfl_sync(0xFFFFFFFFu, my_above, first);
+}
+
+// Adds the histogram of the high byte of `nkeys` (<= 4) keys per thread to hist (shared), using
+// warp match-aggregation so heavily tied scores (bf16 norms take ~100 distinct values) do not
+// serialise on one shared-memory address. Must be called by all 32 lanes of a warp.
+__device__ __forceinline__ void hist_add_hi(uint32_t* hist, const uint16_t* k, const bool* valid,
+                                            int n, int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i < n) {
+            const unsigned bin = valid[i] ? (unsigned)(k[i] >> 8) : 256u;
+            const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
+            if (bin < 256u && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+        }
+    }
+}
+
+// Common tail of every score kernel: keys (and optionally scores) staged in shared memory for
+// one tile -> coalesced global writes + row histogram. skeys/sscores hold kTile entries.
+__device__ __forceinline__ void flush_tile_keys(const uint16_t* skeys, const uint16_t* sscores,
+                                                uint32_t* shist, int row, int tile, int S,
+                                                const Workspace& ws, uint16_t* scores_out) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int s0 = tile * kTile + tid * 4;
+    uint16_t k[4];
+    bool valid[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        k[i] = skeys[tid * 4 + i];
+        valid[i] = (s0 + i) < S;
+        if (!valid[i]) k[i] = 0;
+    }
+    // keys buffer is padded to a multiple of kTile per row: unconditional 8-byte store
+    uint2 packed;
+    packed.x = (uint32_t)k[0] | ((uint32_t)k[1] << 16);
+    packed.y = (uint32_t)k[2] | ((uint32_t)k[3] << 16);
+    *reinterpret_cast<uint2*>(ws.keys + (size_t)row * ws.S_pad + s0) = packed;
+    if (scores_out != nullptr) {
+        uint16_t* dst = scores_out + (size_t)row * S + s0;
+        if (s0 + 3 < S && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+            uint2 sp;
+            sp.x = (uint32_t)sscores[tid * 4] | ((uint32_t)sscores[tid * 4 + 1] << 16);
+            sp.y = (uint32_t)sscores[tid * 4 + 2] | ((uint32_t)sscores[tid * 4 + 3] << 16);
+            *reinterpret_cast<uint2*>(dst) = sp;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (valid[i]) dst[i] = sscores[tid * 4 + i];
+        }
+    }
+    hist_add_hi(shist, k, valid, 4, lane);
+    __syncthreads();
+    if (tid < 256) {
+        const uint32_t c = shist[tid];
+        if (c) atomicAdd(&ws.hist_hi[(size_t)row * 256 + tid], c);
+    }
+}
+
+// ---- launchers implemented in the .cu files (host, C++ linkage) -------------------------------
+cudaError_t launch_knorm_score(const Dims& d, int dtype, const void* K, const Workspace& ws,
+                               void* scores_out, bool want_keys, cudaStream_t st);
+cudaError_t launch_keys_from_scores(const Dims& d, const void* scores, int64_t sb, int64_t sh,
+                                    const Workspace& ws, cudaStream_t st);
+cudaError_t launch_select_compact(const Dims& d, const void* K, const void* V, void* K_out,
+                                  void* V_out, int32_t* idx_out, const Workspace& ws,
+                                  cudaStream_t st);
+cudaError_t launch_streaming_score(const Dims& d, int dtype, int n_sink, void* scores_out,
+                                   cudaStream_t st);
+cudaError_t launch_streaming_compress(const Dims& d, int n_sink, const void* K, const void* V,
+                                      void* K_out, void* V_out, int32_t* idx_out,
+                                      cudaStream_t st);
+
+size_t snapkv_scratch_bytes(const Dims& d, int window);
+cudaError_t launch_snapkv_score(const Dims& d, int dtype, const void* K, const void* q_window,
+                                int window, int kernel_size, const Workspace& ws,
+                                void* scores_out, bool want_keys, cudaStream_t st);
+size_t ea_scratch_bytes(const Dims& d);
+cudaError_t launch_ea_score(const Dims& d, int dtype, const void* K, const void* V, const void* mu,
+                            const void* cov, float eps, int n_sink, int use_vnorm,
+                            const Workspace& ws, void* scores_out, bool want_keys,
+                            cudaStream_t st);
+
+}  // namespace kvp

@@ -1,0 +1,138 @@
+// knorm.cu — stage S for KnormPress and for caller-supplied scores.
+//
+// Reference semantics (kvpress/presses/knorm_press.py:38): scores = -keys.norm(dim=-1)
+//   = -sqrt(sum_d k_d^2), accumulated in fp32, rounded ONCE to the K dtype.
+// One CTA scores one tile of kTile positions of one (b, h) row with 128-bit loads
+// (a sub-warp of LPR lanes per 2*D-byte row, U independent loads in flight per lane), stages
+// the 16-bit ordered keys in shared memory, writes them coalesced and adds the tile's
+// histogram of (key >> 8) to the row histogram the select stage starts from.
+#include "common.cuh"
+
+namespace kvp {
+
+template <typename T, int LPR>
+__global__ void __launch_bounds__(kTileThreads)
+knorm_score_kernel(const T* __restrict__ K, Strides3 ks, int H, int S, int D, Workspace ws,
+                   uint16_t* __restrict__ scores_out, int want_keys) {
+    __shared__ uint16_t skeys[kTile];
+    __shared__ uint16_t sscores[kTile];
+    __shared__ uint32_t shist[256];
+
+    const int tile = blockIdx.x;
+    const int row = blockIdx.y;
+    const int b = row / H, h = row % H;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    shist[tid] = 0;  // kTileThreads == 256
+
+    constexpr int RPW = 32 / LPR;              // rows per warp-wide load
+    constexpr int TOK_PER_WARP = kTile / (kTileThreads / 32);  // 128
+    constexpr int ITERS = TOK_PER_WARP / RPW;
+    constexpr int U = 8;                       // independent 16-byte loads in flight per lane
+    static_assert(ITERS % U == 0, "unroll must divide the iteration count");
+
+    const int sub = lane % LPR;        // which 16-byte chunk of the row
+    const int rsel = lane / LPR;       // which row of the RPW rows
+    const int nvec = D >> 3;           // 16-byte chunks per row
+    const T* base = K + (int64_t)b * ks.b + (int64_t)h * ks.h + (int64_t)sub * 8;
+    const int s_warp = tile * kTile + warp * TOK_PER_WARP;
+    const uint64_t pol_keep = l2_policy_evict_last();
+
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it += U) {
+        int4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int s = s_warp + (it + u) * RPW + rsel;
+            v[u] = make_int4(0, 0, 0, 0);
+            if (s < S && sub < nvec) v[u] = ldg_hint(base + (int64_t)s * ks.s, pol_keep);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t w[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z,
+                                   (uint32_t)v[u].w};
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = F16Traits<T>::unpack2(w[j]);
+                ss = fmaf(f.x, f.x, ss);
+                ss = fmaf(f.y, f.y, ss);
+            }
+#pragma unroll
+            for (int off = LPR / 2; off >= 1; off >>= 1)
+                ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
+            if (sub == 0) {
+                const int sl = warp * TOK_PER_WARP + (it + u) * RPW + rsel;
+                // -sqrt(ss) rounded once to the storage dtype (negation is exact)
+                const uint16_t bits = F16Traits<T>::from_float(sqrtf(ss)) ^ 0x8000u;
+                sscores[sl] = bits;
+                skeys[sl] = ordered_key16(bits);
+            }
+        }
+    }
+    __syncthreads();
+    if (want_keys) {
+        flush_tile_keys(skeys, sscores, shist, row, tile, S, ws, scores_out);
+    } else {
+        // score-only call: just write the scores
+        const int s0 = tile * kTile + tid * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (s0 + i < S) scores_out[(size_t)row * S + s0 + i] = sscores[tid * 4 + i];
+    }
+}
+
+template <typename T>
+static cudaError_t launch_knorm_t(const Dims& d, const void* K, const Workspace& ws,
+                                  void* scores_out, bool want_keys, cudaStream_t st) {
+    const int n_tiles = (d.S + kTile - 1) / kTile;
+    dim3 grid(n_tiles, d.R);
+    const int nvec = d.D / 8;
+    const T* Kp = static_cast<const T*>(K);
+    uint16_t* so = static_cast<uint16_t*>(scores_out);
+#define KVP_LAUNCH_KNORM(LPR)                                                                   \
+    knorm_score_kernel<T, LPR><<<grid, kTileThreads, 0, st>>>(Kp, d.ks, d.H, d.S, d.D, ws, so, \
+                                                              want_keys ? 1 : 0)
+    if (nvec <= 4) KVP_LAUNCH_KNORM(4);
+    else if (nvec <= 8) KVP_LAUNCH_KNORM(8);
+    else if (nvec <= 16) KVP_LAUNCH_KNORM(16);
+    else KVP_LAUNCH_KNORM(32);
+#undef KVP_LAUNCH_KNORM
+    return cudaPeekAtLastError();
+}
+
+cudaError_t launch_knorm_score(const Dims& d, int dtype, const void* K, const Workspace& ws,
+                               void* scores_out, bool want_keys, cudaStream_t st) {
+    if (dtype == KVP_BF16)
+        return launch_knorm_t<__nv_bfloat16>(d, K, ws, scores_out, want_keys, st);
+    return launch_knorm_t<__half>(d, K, ws, scores_out, want_keys, st);
+}
+
+// ---- caller-supplied scores -> keys + histogram ------------------------------------------------
+__global__ void __launch_bounds__(kTileThreads)
+keys_from_scores_kernel(const uint16_t* __restrict__ scores, int64_t sb, int64_t sh, int H, int S,
+                        Workspace ws) {
+    __shared__ uint16_t skeys[kTile];
+    __shared__ uint32_t shist[256];
+    const int tile = blockIdx.x, row = blockIdx.y, tid = threadIdx.x;
+    const int b = row / H, h = row % H;
+    shist[tid] = 0;
+    const uint16_t* src = scores + (int64_t)b * sb + (int64_t)h * sh;
+    const int s0 = tile * kTile + tid * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        skeys[tid * 4 + i] = (s0 + i < S) ? ordered_key16(src[s0 + i]) : (uint16_t)0;
+    __syncthreads();
+    flush_tile_keys(skeys, nullptr, shist, row, tile, S, ws, nullptr);
+}
+
+cudaError_t launch_keys_from_scores(const Dims& d, const void* scores, int64_t sb, int64_t sh,
+                                    const Workspace& ws, cudaStream_t st) {
+    const int n_tiles = (d.S + kTile - 1) / kTile;
+    dim3 grid(n_tiles, d.R);
+    keys_from_scores_kernel<<<grid, kTileThreads, 0, st>>>(static_cast<const uint16_t*>(scores),
+                                                           sb, sh, d.H, d.S, ws);
+    return cudaPeekAtLastError();
+}
+
+}  // namespace kvp

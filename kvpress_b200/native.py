@@ -1,0 +1,399 @@
+"""ctypes binding of libkvpress_b200.so (the C ABI in include/kvpress_b200.h).
+
+torch is used here only as the owner of device memory and streams: tensors are handed to the
+library as raw pointers + element strides, outputs and scratch are allocated with torch's caching
+allocator, kernels are enqueued on torch's current stream. There is NO fallback: if the shared
+library is missing or a tensor is not a CUDA tensor, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+_LIB_NAME = "libkvpress_b200.so"
+_LIB_PATH = Path(__file__).resolve().parent / _LIB_NAME
+
+SCORER_GENERIC, SCORER_KNORM, SCORER_STREAMING, SCORER_SNAPKV, SCORER_EXPECTED_ATTENTION = range(5)
+_DTYPES = {torch.bfloat16: 0, torch.float16: 1}
+
+
+class KvpProblem(ctypes.Structure):
+    """Mirror of `struct kvp_problem`."""
+
+    _fields_ = [
+        ("B", ctypes.c_int32),
+        ("Hkv", ctypes.c_int32),
+        ("Hq", ctypes.c_int32),
+        ("S", ctypes.c_int32),
+        ("D", ctypes.c_int32),
+        ("n_kept", ctypes.c_int32),
+        ("dtype", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("k_stride", ctypes.c_int64 * 3),
+        ("v_stride", ctypes.c_int64 * 3),
+    ]
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); every symbol include/kvpress_b200.h declares
+_P = ctypes.c_void_p
+_PP = ctypes.POINTER(KvpProblem)
+_SZ = ctypes.c_size_t
+_I = ctypes.c_int32
+SIGNATURES = {
+    "kvp_abi_version": (ctypes.c_int, []),
+    "kvp_status_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "kvp_last_cuda_error": (ctypes.c_char_p, []),
+    "kvp_workspace_bytes": (ctypes.c_int, [_PP, ctypes.c_int, ctypes.POINTER(_SZ)]),
+    "kvp_launches_per_compress": (ctypes.c_int, [_PP, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "kvp_knorm_score": (ctypes.c_int, [_PP, _P, _P, _P]),
+    "kvp_knorm_compress": (ctypes.c_int, [_PP, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "kvp_streaming_score": (ctypes.c_int, [_PP, _I, _P, _P]),
+    "kvp_streaming_compress": (ctypes.c_int, [_PP, _I, _P, _P, _P, _P, _P, _P]),
+    "kvp_snapkv_score": (ctypes.c_int, [_PP, _P, _P, _I, _I, _P, _P, _SZ, _P]),
+    "kvp_snapkv_compress": (ctypes.c_int, [_PP, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    "kvp_expected_attention_score": (
+        ctypes.c_int, [_PP, _P, _P, _P, _P, ctypes.c_float, _I, _I, _P, _P, _SZ, _P]),
+    "kvp_expected_attention_compress": (
+        ctypes.c_int, [_PP, _P, _P, _P, _P, ctypes.c_float, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    "kvp_scores_compress": (
+        ctypes.c_int, [_PP, _P, ctypes.POINTER(ctypes.c_int64), _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "kvp_host_workspace_bytes": (ctypes.c_int, [_PP, ctypes.c_int, ctypes.POINTER(_SZ)]),
+    "kvp_knorm_compress_host": (ctypes.c_int, [_PP, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def library_path() -> Path:
+    return Path(os.environ.get("KVPRESS_B200_LIB", _LIB_PATH))
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once) and bind every declared symbol. Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.exists():
+        raise NativeLibraryError(
+            f"{path} not found: build it with `python -m kvpress_b200.build` (needs nvcc). "
+            "kvpress_b200 has no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(str(path))
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.kvp_abi_version() != 1:
+        raise NativeLibraryError(f"ABI version mismatch: library reports {lib.kvp_abi_version()}")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        lib = load()
+        msg = lib.kvp_status_string(rc).decode()
+        if rc == -6:
+            msg += ": " + lib.kvp_last_cuda_error().decode()
+        raise RuntimeError(f"{what} failed: {msg} (status {rc})")
+
+
+def _require_cuda_kv(keys: torch.Tensor, values: torch.Tensor) -> None:
+    if not (keys.is_cuda and values.is_cuda):
+        raise RuntimeError(
+            "kvpress_b200 runs on CUDA tensors only (sm_100a kernels); got "
+            f"keys on {keys.device}, values on {values.device}. There is no CPU path."
+        )
+    if keys.dtype not in _DTYPES or values.dtype != keys.dtype:
+        raise RuntimeError(f"kvpress_b200 supports bf16/fp16 caches, got {keys.dtype}/{values.dtype}")
+    if keys.dim() != 4 or values.shape != keys.shape:
+        raise RuntimeError(f"expected K, V of shape [B, Hkv, S, D], got {tuple(keys.shape)}, {tuple(values.shape)}")
+
+
+def _rows_ok(t: torch.Tensor) -> bool:
+    if t.stride(3) != 1 or t.data_ptr() % 16:
+        return False
+    for dim in range(3):
+        if t.shape[dim] > 1 and (t.stride(dim) % 8 or t.stride(dim) < 0):
+            return False
+    return t.shape[2] == 1 or t.stride(2) >= t.shape[3]
+
+
+def _normalise(t: torch.Tensor) -> torch.Tensor:
+    """Strided views are consumed as they are; only layouts the kernels cannot address are copied."""
+    return t if _rows_ok(t) else t.contiguous()
+
+
+def _strides(t: torch.Tensor):
+    return tuple(int(t.stride(d)) if t.shape[d] > 1 else 0 for d in range(3))
+
+
+def make_problem(keys: torch.Tensor, values: torch.Tensor, n_kept: int, num_q_heads: Optional[int] = None) -> KvpProblem:
+    B, H, S, D = keys.shape
+    p = KvpProblem()
+    p.B, p.Hkv, p.S, p.D = B, H, S, D
+    p.Hq = int(num_q_heads) if num_q_heads else H
+    p.n_kept = int(n_kept)
+    p.dtype = _DTYPES[keys.dtype]
+    ks, vs = _strides(keys), _strides(values)
+    # a row stride of 0 only happens for S == 1; keep it addressable
+    p.k_stride = (ctypes.c_int64 * 3)(ks[0], ks[1], ks[2] if S > 1 else D)
+    p.v_stride = (ctypes.c_int64 * 3)(vs[0], vs[1], vs[2] if S > 1 else D)
+    return p
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def workspace_bytes(p: KvpProblem, scorer: int) -> int:
+    out = _SZ(0)
+    _check(load().kvp_workspace_bytes(ctypes.byref(p), scorer, ctypes.byref(out)), "kvp_workspace_bytes")
+    return int(out.value)
+
+
+def launches_per_compress(p: KvpProblem, scorer: int) -> int:
+    out = ctypes.c_int(0)
+    _check(load().kvp_launches_per_compress(ctypes.byref(p), scorer, ctypes.byref(out)), "kvp_launches_per_compress")
+    return int(out.value)
+
+
+def _alloc_out(keys: torch.Tensor, n_kept: int, want_idx: bool, want_scores: bool):
+    B, H, S, D = keys.shape
+    k_out = torch.empty((B, H, n_kept, D), dtype=keys.dtype, device=keys.device)
+    v_out = torch.empty_like(k_out)
+    idx = torch.empty((B, H, n_kept), dtype=torch.int32, device=keys.device) if want_idx else None
+    scores = torch.empty((B, H, S), dtype=keys.dtype, device=keys.device) if want_scores else None
+    return k_out, v_out, idx, scores
+
+
+def _workspace(p: KvpProblem, scorer: int, device) -> torch.Tensor:
+    return torch.empty(workspace_bytes(p, scorer), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------------------
+# Knorm
+# --------------------------------------------------------------------------------------------------
+def knorm_score(keys: torch.Tensor) -> torch.Tensor:
+    _require_cuda_kv(keys, keys)
+    keys = _normalise(keys)
+    p = make_problem(keys, keys, 0)
+    scores = torch.empty(keys.shape[:3], dtype=keys.dtype, device=keys.device)
+    with torch.cuda.device(keys.device):
+        _check(load().kvp_knorm_score(ctypes.byref(p), _ptr(keys), _ptr(scores), _stream()), "kvp_knorm_score")
+    return scores
+
+
+def knorm_compress(keys, values, n_kept: int, return_indices: bool = False, return_scores: bool = False):
+    _require_cuda_kv(keys, values)
+    keys, values = _normalise(keys), _normalise(values)
+    p = make_problem(keys, values, n_kept)
+    k_out, v_out, idx, scores = _alloc_out(keys, n_kept, return_indices, return_scores)
+    if n_kept > 0:
+        with torch.cuda.device(keys.device):
+            ws = _workspace(p, SCORER_KNORM, keys.device)
+            _check(
+                load().kvp_knorm_compress(
+                    ctypes.byref(p), _ptr(keys), _ptr(values), _ptr(k_out), _ptr(v_out), _ptr(idx), _ptr(scores),
+                    _ptr(ws), ws.numel(), _stream()),
+                "kvp_knorm_compress",
+            )
+    return k_out, v_out, idx, scores
+
+
+# --------------------------------------------------------------------------------------------------
+# StreamingLLM
+# --------------------------------------------------------------------------------------------------
+def streaming_score(keys: torch.Tensor, n_kept: int, n_sink: int) -> torch.Tensor:
+    _require_cuda_kv(keys, keys)
+    p = make_problem(keys, keys, n_kept)
+    scores = torch.empty(keys.shape[:3], dtype=keys.dtype, device=keys.device)
+    with torch.cuda.device(keys.device):
+        _check(load().kvp_streaming_score(ctypes.byref(p), n_sink, _ptr(scores), _stream()), "kvp_streaming_score")
+    return scores
+
+
+def streaming_compress(keys, values, n_kept: int, n_sink: int, return_indices: bool = False):
+    _require_cuda_kv(keys, values)
+    keys, values = _normalise(keys), _normalise(values)
+    p = make_problem(keys, values, n_kept)
+    k_out, v_out, idx, _ = _alloc_out(keys, n_kept, return_indices, False)
+    if n_kept > 0:
+        with torch.cuda.device(keys.device):
+            _check(
+                load().kvp_streaming_compress(
+                    ctypes.byref(p), n_sink, _ptr(keys), _ptr(values), _ptr(k_out), _ptr(v_out), _ptr(idx), _stream()),
+                "kvp_streaming_compress",
+            )
+    return k_out, v_out, idx
+
+
+# --------------------------------------------------------------------------------------------------
+# SnapKV
+# --------------------------------------------------------------------------------------------------
+def _check_q(q_window: torch.Tensor, keys: torch.Tensor, window: int):
+    B, _, _, D = keys.shape
+    if q_window.dim() != 4 or q_window.shape[0] != B or q_window.shape[2] != window or q_window.shape[3] != D:
+        raise RuntimeError(f"q_window must be [B, Hq, {window}, {D}], got {tuple(q_window.shape)}")
+    if q_window.dtype != keys.dtype or q_window.device != keys.device:
+        raise RuntimeError("q_window must share dtype and device with the keys")
+    return q_window.contiguous()
+
+
+def snapkv_score(keys, q_window, window: int, kernel_size: int) -> torch.Tensor:
+    _require_cuda_kv(keys, keys)
+    keys = _normalise(keys)
+    q_window = _check_q(q_window, keys, window)
+    p = make_problem(keys, keys, 0, q_window.shape[1])
+    scores = torch.empty(keys.shape[:3], dtype=keys.dtype, device=keys.device)
+    with torch.cuda.device(keys.device):
+        ws = _workspace(p, SCORER_SNAPKV, keys.device)
+        _check(
+            load().kvp_snapkv_score(
+                ctypes.byref(p), _ptr(keys), _ptr(q_window), window, kernel_size, _ptr(scores), _ptr(ws), ws.numel(),
+                _stream()),
+            "kvp_snapkv_score",
+        )
+    return scores
+
+
+def snapkv_compress(keys, values, q_window, window: int, kernel_size: int, n_kept: int,
+                    return_indices: bool = False, return_scores: bool = False):
+    _require_cuda_kv(keys, values)
+    keys, values = _normalise(keys), _normalise(values)
+    q_window = _check_q(q_window, keys, window)
+    p = make_problem(keys, values, n_kept, q_window.shape[1])
+    k_out, v_out, idx, scores = _alloc_out(keys, n_kept, return_indices, return_scores)
+    if n_kept > 0:
+        with torch.cuda.device(keys.device):
+            ws = _workspace(p, SCORER_SNAPKV, keys.device)
+            _check(
+                load().kvp_snapkv_compress(
+                    ctypes.byref(p), _ptr(keys), _ptr(values), _ptr(q_window), window, kernel_size, _ptr(k_out),
+                    _ptr(v_out), _ptr(idx), _ptr(scores), _ptr(ws), ws.numel(), _stream()),
+                "kvp_snapkv_compress",
+            )
+    return k_out, v_out, idx, scores
+
+
+# --------------------------------------------------------------------------------------------------
+# ExpectedAttention
+# --------------------------------------------------------------------------------------------------
+def _check_stats(mu, cov, keys):
+    B, _, _, D = keys.shape
+    if mu.dim() != 3 or mu.shape[0] != B or mu.shape[2] != D:
+        raise RuntimeError(f"mu must be [B, Hq, {D}], got {tuple(mu.shape)}")
+    mu = mu.to(keys.dtype).contiguous()
+    if cov is not None:
+        if tuple(cov.shape) != (B, mu.shape[1], D, D):
+            raise RuntimeError(f"cov must be [B, Hq, {D}, {D}], got {tuple(cov.shape)}")
+        cov = cov.to(keys.dtype).contiguous()
+    return mu, cov
+
+
+def expected_attention_score(keys, values, mu, cov, epsilon: float, n_sink: int, use_vnorm: bool) -> torch.Tensor:
+    _require_cuda_kv(keys, values)
+    keys, values = _normalise(keys), _normalise(values)
+    mu, cov = _check_stats(mu, cov, keys)
+    p = make_problem(keys, values, 0, mu.shape[1])
+    scores = torch.empty(keys.shape[:3], dtype=keys.dtype, device=keys.device)
+    with torch.cuda.device(keys.device):
+        ws = _workspace(p, SCORER_EXPECTED_ATTENTION, keys.device)
+        _check(
+            load().kvp_expected_attention_score(
+                ctypes.byref(p), _ptr(keys), _ptr(values), _ptr(mu), _ptr(cov), float(epsilon), n_sink,
+                int(bool(use_vnorm)), _ptr(scores), _ptr(ws), ws.numel(), _stream()),
+            "kvp_expected_attention_score",
+        )
+    return scores
+
+
+def expected_attention_compress(keys, values, mu, cov, epsilon: float, n_sink: int, use_vnorm: bool, n_kept: int,
+                                return_indices: bool = False, return_scores: bool = False):
+    _require_cuda_kv(keys, values)
+    keys, values = _normalise(keys), _normalise(values)
+    mu, cov = _check_stats(mu, cov, keys)
+    p = make_problem(keys, values, n_kept, mu.shape[1])
+    k_out, v_out, idx, scores = _alloc_out(keys, n_kept, return_indices, return_scores)
+    if n_kept > 0:
+        with torch.cuda.device(keys.device):
+            ws = _workspace(p, SCORER_EXPECTED_ATTENTION, keys.device)
+            _check(
+                load().kvp_expected_attention_compress(
+                    ctypes.byref(p), _ptr(keys), _ptr(values), _ptr(mu), _ptr(cov), float(epsilon), n_sink,
+                    int(bool(use_vnorm)), _ptr(k_out), _ptr(v_out), _ptr(idx), _ptr(scores), _ptr(ws), ws.numel(),
+                    _stream()),
+                "kvp_expected_attention_compress",
+            )
+    return k_out, v_out, idx, scores
+
+
+# --------------------------------------------------------------------------------------------------
+# generic scores (wrapper presses, user-defined ScorerPress subclasses)
+# --------------------------------------------------------------------------------------------------
+def scores_compress(scores: torch.Tensor, keys, values, n_kept: int, return_indices: bool = False):
+    _require_cuda_kv(keys, values)
+    keys, values = _normalise(keys), _normalise(values)
+    if tuple(scores.shape) != tuple(keys.shape[:3]) or scores.device != keys.device:
+        raise RuntimeError(f"scores must be [B, Hkv, S] on the cache device, got {tuple(scores.shape)}")
+    scores = scores.to(keys.dtype)
+    if scores.stride(2) != 1:
+        scores = scores.contiguous()
+    p = make_problem(keys, values, n_kept)
+    k_out, v_out, idx, _ = _alloc_out(keys, n_kept, return_indices, False)
+    if n_kept > 0:
+        sstride = (ctypes.c_int64 * 2)(
+            scores.stride(0) if scores.shape[0] > 1 else 0, scores.stride(1) if scores.shape[1] > 1 else 0)
+        with torch.cuda.device(keys.device):
+            ws = _workspace(p, SCORER_GENERIC, keys.device)
+            _check(
+                load().kvp_scores_compress(
+                    ctypes.byref(p), _ptr(scores), sstride, _ptr(keys), _ptr(values), _ptr(k_out), _ptr(v_out),
+                    _ptr(idx), _ptr(ws), ws.numel(), _stream()),
+                "kvp_scores_compress",
+            )
+    return k_out, v_out, idx
+
+
+# --------------------------------------------------------------------------------------------------
+# host-buffer end-to-end path (bench.py `e2e`)
+# --------------------------------------------------------------------------------------------------
+def knorm_compress_host(keys_host: torch.Tensor, values_host: torch.Tensor, n_kept: int, device, workspace=None,
+                        out=None):
+    """K, V are contiguous HOST tensors (ideally pinned); K', V' come back as host tensors."""
+    if keys_host.is_cuda or values_host.is_cuda or not keys_host.is_contiguous() or not values_host.is_contiguous():
+        raise RuntimeError("knorm_compress_host takes contiguous host tensors")
+    B, H, S, D = keys_host.shape
+    p = KvpProblem()
+    p.B, p.Hkv, p.Hq, p.S, p.D, p.n_kept, p.dtype = B, H, H, S, D, int(n_kept), _DTYPES[keys_host.dtype]
+    lib = load()
+    need = _SZ(0)
+    _check(lib.kvp_host_workspace_bytes(ctypes.byref(p), SCORER_KNORM, ctypes.byref(need)), "kvp_host_workspace_bytes")
+    with torch.cuda.device(device):
+        if workspace is None or workspace.numel() < need.value:
+            workspace = torch.empty(need.value, dtype=torch.uint8, device=device)
+        if out is None:
+            k_out = torch.empty((B, H, n_kept, D), dtype=keys_host.dtype).pin_memory()
+            v_out = torch.empty_like(k_out).pin_memory()
+        else:
+            k_out, v_out = out
+        _check(
+            lib.kvp_knorm_compress_host(
+                ctypes.byref(p), _ptr(keys_host), _ptr(values_host), _ptr(k_out), _ptr(v_out), None, _ptr(workspace),
+                workspace.numel(), _stream()),
+            "kvp_knorm_compress_host",
+        )
+    return k_out, v_out, workspace

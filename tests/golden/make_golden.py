@@ -1,0 +1,135 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference)
+on CPU for seeded inputs. Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Harness shims: a stub `fire` module (kvpress imports it at package import for an
+unrelated CLI) — nothing in the reference is modified. 16-bit tensors are stored as uint16 views.
+"""
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = Path(__file__).resolve().parent
+
+
+def import_reference():
+    sys.modules.setdefault("fire", types.ModuleType("fire"))
+    sys.path.insert(0, REF)
+    import kvpress  # noqa
+
+    return kvpress
+
+
+def u16(t: torch.Tensor) -> np.ndarray:
+    assert t.dtype in (torch.bfloat16, torch.float16)
+    return t.contiguous().view(torch.uint16).numpy()
+
+
+def make_case(name, *, B, Hq, Hkv, D, hidden, S, seed, dtype=torch.bfloat16, heavy_tail=False):
+    kvpress = import_reference()
+    from transformers import LlamaConfig
+    from transformers.models.llama.modeling_llama import LlamaAttention, LlamaRotaryEmbedding
+
+    torch.manual_seed(seed)
+    cfg = LlamaConfig(hidden_size=hidden, num_attention_heads=Hq, num_key_value_heads=Hkv, head_dim=D,
+                      num_hidden_layers=1, intermediate_size=2 * hidden, vocab_size=128,
+                      max_position_embeddings=8192)
+    cfg._attn_implementation = "sdpa"
+    attn = LlamaAttention(cfg, 0).to(dtype).eval()
+    attn.rotary_emb = LlamaRotaryEmbedding(cfg)
+    hidden_states = torch.randn(B, S, hidden).to(dtype)
+    keys = torch.randn(B, Hkv, S, D).to(dtype)
+    values = torch.randn(B, Hkv, S, D).to(dtype)
+    if heavy_tail:  # a few huge-norm "sink" keys and exact duplicates -> forced ties
+        keys[:, :, :3] *= 10
+        keys[:, :, 50:60] = keys[:, :, 40:50]
+    cos, sin = attn.rotary_emb(hidden_states, torch.arange(S)[None])
+    pe = (cos, sin)
+    kwargs = {"position_embeddings": pe}
+    out = {
+        "meta": np.array([B, Hq, Hkv, D, hidden, S, seed], dtype=np.int64),
+        "hidden_states": u16(hidden_states), "keys": u16(keys), "values": u16(values),
+        "q_weight": u16(attn.q_proj.weight.detach()), "cos": u16(cos), "sin": u16(sin),
+    }
+    ratios = [0.1, 0.25, 0.5, 0.7, 0.875]
+    out["ratios"] = np.array(ratios)
+
+    with torch.no_grad():
+        # ---- Knorm ---------------------------------------------------------------------------
+        press = kvpress.KnormPress()
+        out["knorm_scores"] = u16(press.score(attn, hidden_states, keys, values, None, kwargs))
+        # ---- StreamingLLM ----------------------------------------------------------------------
+        for i, r in enumerate(ratios):
+            press = kvpress.StreamingLLMPress(compression_ratio=r, n_sink=4)
+            sc = press.score(attn, hidden_states, keys, values, None, kwargs)
+            out[f"streaming_scores_{i}"] = u16(sc)
+        # ---- SnapKV ------------------------------------------------------------------------------
+        from kvpress.presses.snapkv_press import SnapKVPress
+        from kvpress.utils import get_prerope_query_states
+        from transformers.models.llama.modeling_llama import rotate_half
+
+        w = 64 if S > 128 else 16
+        snap = SnapKVPress(window_size=w, kernel_size=5)
+        q = get_prerope_query_states(attn, hidden_states[:, -w:])
+        q_window = (q * cos[:, -w:].unsqueeze(1)) + (rotate_half(q) * sin[:, -w:].unsqueeze(1))
+        out["snap_window"] = np.array([w, 5])
+        out["snap_q_window"] = u16(q_window)
+        out["snap_scores"] = u16(snap.score(attn, hidden_states, keys, values, None, kwargs))
+        # ---- ExpectedAttention ---------------------------------------------------------------------
+        ea = kvpress.ExpectedAttentionPress(n_sink=4, n_future_positions=512, use_covariance=True, use_vnorm=True)
+        mu, cov = ea.get_query_statistics(attn, hidden_states)
+        out["ea_mu"], out["ea_cov"] = u16(mu), u16(cov)
+        fut = torch.arange(S, S + 512)[None]
+        cf, sf = attn.rotary_emb(mu, fut)
+        out["ea_cos_future"], out["ea_sin_future"] = u16(cf[0]), u16(sf[0])
+        out["ea_scores"] = u16(ea.score(attn, hidden_states, keys, values, None, kwargs))
+        ea2 = kvpress.ExpectedAttentionPress(n_sink=4, use_covariance=False, use_vnorm=False, epsilon=0.0)
+        out["ea_scores_nocov_novnorm"] = u16(ea2.score(attn, hidden_states, keys, values, None, kwargs))
+        ea3 = kvpress.ExpectedAttentionPress(n_sink=4, use_covariance=True, use_vnorm=True, epsilon=1e-2)
+        out["ea_scores_eps"] = u16(ea3.score(attn, hidden_states, keys, values, None, kwargs))
+
+        # ---- full compress(): kept index sets (sorted) and gathered rows checksum -----------------
+        for i, r in enumerate(ratios):
+            for tag, press in (
+                ("knorm", kvpress.KnormPress(compression_ratio=r)),
+                ("streaming", kvpress.StreamingLLMPress(compression_ratio=r, n_sink=4)),
+                ("snap", SnapKVPress(compression_ratio=r, window_size=w, kernel_size=5)),
+                ("ea", kvpress.ExpectedAttentionPress(compression_ratio=r)),
+            ):
+                sc = press.score(attn, hidden_states, keys, values, None, kwargs)
+                n_kept = int(S * (1 - r))
+                idx = sc.topk(n_kept, dim=-1).indices
+                k2, v2 = press.compress(attn, hidden_states, keys, values, None, kwargs)
+                assert k2.shape[2] == n_kept
+                # the reference's own output must be the gather of its own top-k
+                g = keys.gather(2, idx.unsqueeze(-1).expand(-1, -1, -1, D))
+                assert torch.equal(g, k2)
+                out[f"{tag}_kept_{i}"] = idx.sort(-1).values.numpy().astype(np.int32)
+    np.savez_compressed(OUT / f"{name}.npz", **out)
+    print(name, {k: v.shape for k, v in out.items() if k.endswith("scores")})
+
+
+def make_decoding_table():
+    """decoding_press.py:194-236 — ratio bisection table."""
+    kvpress = import_reference()
+    press = kvpress.DecodingPress(base_press=kvpress.KnormPress(), compression_interval=4, target_size=54)
+    rows = []
+    for q_len, target in [(58, 54), (108, 54), (2560, 2048), (4607, 2048), (4096 + 37 + 511, 2048), (100, 200),
+                          (131072, 39321), (2049, 2048), (3000, 1), (7, 3)]:
+        r = press._find_target_compression_ratio(q_len, target)
+        rows.append((q_len, target, r, int(q_len * (1 - r))))
+    np.savez(OUT / "decoding_ratio.npz", table=np.array(rows, dtype=np.float64))
+    print("decoding table", rows[:3])
+
+
+if __name__ == "__main__":
+    make_case("small64", B=2, Hq=4, Hkv=2, D=64, hidden=256, S=384, seed=11)
+    make_case("llama128", B=1, Hq=8, Hkv=2, D=128, hidden=512, S=1200, seed=12)
+    make_case("ties128", B=1, Hq=4, Hkv=1, D=128, hidden=256, S=2500, seed=13, heavy_tail=True)
+    make_case("half64", B=1, Hq=2, Hkv=2, D=64, hidden=128, S=300, seed=14, dtype=torch.float16)
+    make_decoding_table()

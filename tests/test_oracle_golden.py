@@ -1,0 +1,105 @@
+"""The CPU oracle (oracle/press_oracle.py) against the golden vectors produced by the imported
+reference (tests/golden/make_golden.py). This is what pins the oracle; the GPU parity tests then
+compare the CUDA path against the oracle and against the same golden files."""
+import numpy as np
+import torch
+
+from oracle import press_oracle as O
+from tests.conftest import GOLDEN_DIR, ulp16_diff
+
+
+def test_knorm_scores_match_reference(golden):
+    got = O.knorm_scores(golden.t("keys"))
+    assert torch.equal(got, golden.t("knorm_scores"))
+
+
+def test_streaming_scores_and_kept_sets(golden):
+    keys = golden.t("keys")
+    for i, r in enumerate(golden.ratios):
+        assert torch.equal(O.streaming_scores(keys, r, 4), golden.t(f"streaming_scores_{i}"))
+        n_kept = O.kept_count(golden.S, r)
+        ref_kept = golden.t(f"streaming_kept_{i}")
+        want = O.streaming_kept(golden.S, n_kept, 4).to(torch.int32)
+        assert torch.equal(ref_kept, want.expand_as(ref_kept))
+
+
+def test_snapkv_prologue_and_scores(golden):
+    w, ksz = (int(x) for x in golden.z["snap_window"])
+    q = O.snapkv_window_queries(golden.t("hidden_states"), golden.t("q_weight"), golden.Hq, golden.D,
+                                golden.t("cos"), golden.t("sin"), w)
+    assert torch.equal(q, golden.t("snap_q_window"))
+    got = O.snapkv_scores(q, golden.t("keys"), w, ksz)
+    assert torch.equal(got, golden.t("snap_scores"))
+
+
+def test_snapkv_fp32_restatement_is_close_to_reference(golden):
+    w, ksz = (int(x) for x in golden.z["snap_window"])
+    hi = O.snapkv_scores_fp32(golden.t("snap_q_window"), golden.t("keys"), w, ksz)[..., :-w]
+    ref = golden.t("snap_scores")[..., :-w].float()
+    # the reference rounds to 16 bit at ~7 points; its scores sit within a few 16-bit ulps of fp32 math
+    rel = ((hi - ref).abs() / hi.abs().clamp_min(1e-30))
+    assert rel.max() < 3e-2 and rel.mean() < 4e-3
+
+
+def test_expected_attention_stats_and_scores(golden):
+    mu, cov = O.expected_attention_stats(golden.t("hidden_states"), golden.t("q_weight"), golden.Hq, golden.D,
+                                         golden.t("ea_cos_future"), golden.t("ea_sin_future"), 4)
+    assert torch.equal(mu, golden.t("ea_mu"))
+    assert torch.equal(cov, golden.t("ea_cov"))
+    k, v = golden.t("keys"), golden.t("values")
+    assert torch.equal(O.expected_attention_scores(k, v, mu, cov, 0.0, 4, True), golden.t("ea_scores"))
+    assert torch.equal(O.expected_attention_scores(k, v, mu, None, 0.0, 4, False),
+                       golden.t("ea_scores_nocov_novnorm"))
+    assert torch.equal(O.expected_attention_scores(k, v, mu, cov, 1e-2, 4, True), golden.t("ea_scores_eps"))
+
+
+def test_kept_sets_match_reference_topk(golden):
+    """oracle top-k + gather == the reference's compress() output sets, and the kernels' canonical
+    lowest-position tie rule is a VALID answer w.r.t. the reference scores."""
+    k, v = golden.t("keys"), golden.t("values")
+    score_of = {
+        "knorm": golden.t("knorm_scores"),
+        "snap": golden.t("snap_scores"),
+        "ea": golden.t("ea_scores"),
+    }
+    for i, r in enumerate(golden.ratios):
+        n_kept = O.kept_count(golden.S, r)
+        for tag, sc in score_of.items():
+            k2, v2, idx = O.compress_with_scores(sc, k, v, n_kept)
+            ref = golden.t(f"{tag}_kept_{i}")
+            assert torch.equal(idx.sort(-1).values.to(torch.int32), ref), (tag, r)
+            assert torch.equal(k2, O.gather_rows(k, idx)) and torch.equal(v2, O.gather_rows(v, idx))
+            canon = O.select_lowest_index_ties(sc, n_kept)
+            assert O.check_selection(sc, canon, n_kept)["ok"], (tag, r)
+            # and the reference's own set passes the same tie-aware check
+            assert O.check_selection(sc, ref.long(), n_kept)["ok"]
+
+
+def test_check_selection_rejects_wrong_sets(golden):
+    sc = golden.t("knorm_scores")
+    n_kept = golden.S // 2
+    canon = O.select_lowest_index_ties(sc, n_kept)
+    bad = canon.clone()
+    worst = sc.float().argmin(-1)
+    bad[..., 0] = worst  # swap in the worst-scoring position
+    assert not O.check_selection(sc, bad, n_kept)["ok"]
+
+
+def test_decoding_ratio_table():
+    table = np.load(GOLDEN_DIR / "decoding_ratio.npz")["table"]
+    for q_len, target, ratio, kept in table:
+        got = O.find_target_compression_ratio(int(q_len), int(target))
+        assert got == ratio
+        assert O.kept_count(int(q_len), got) == int(kept)
+
+
+def test_kept_count_float64_arithmetic():
+    assert O.kept_count(131072, 0.7) == 39321  # 1 - 0.7 = 0.30000000000000004
+    assert O.kept_count(23, 0.4) == 13
+    assert O.kept_count(108, 0.5) == 54
+
+
+def test_ulp_helper():
+    a = torch.tensor([1.0, -1.0, 0.0], dtype=torch.bfloat16)
+    b = torch.tensor([1.0078125, -1.0078125, -0.0], dtype=torch.bfloat16)
+    assert ulp16_diff(a, b).tolist() == [1, 1, 0]
