@@ -324,7 +324,7 @@ int kvp_scores_compress(const kvp_problem* p, const void* scores, const int64_t*
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaMemsetAsync(ws.hist_hi, 0, L.hist_bytes, st);
     if (e != cudaSuccess) return fail_cuda(e);
-    e = launch_keys_from_scores(d, scores, score_stride[0], score_stride[1], ws, st);
+    e = launch_keys_from_scores(d, p->dtype, scores, score_stride[0], score_stride[1], ws, st);
     if (e != cudaSuccess) return fail_cuda(e);
     return select_and_compact(d, K, V, K_out, V_out, idx_out, ws, st);
 }

@@ -39,8 +39,11 @@ struct Dims {
 };
 
 // ---- 16-bit float -> ordered unsigned key (same for bf16 and fp16: sign-magnitude) --------
-__host__ __device__ __forceinline__ uint16_t ordered_key16(uint16_t bits) {
-    if (bits == 0x8000u) bits = 0;  // -0 == +0 (torch.topk compares by value)
+// inf_bits = 0x7F80 for bf16, 0x7C00 for fp16: anything above it (either sign) is a NaN, which
+// torch.topk ranks above every number -> largest key.
+__host__ __device__ __forceinline__ uint16_t ordered_key16(uint16_t bits, uint16_t inf_bits) {
+    if ((bits & 0x7FFFu) > inf_bits) return 0xFFFFu;  // NaN
+    if (bits == 0x8000u) bits = 0;                    // -0 == +0 (torch.topk compares by value)
     return (bits & 0x8000u) ? (uint16_t)(~bits) : (uint16_t)(bits | 0x8000u);
 }
 __host__ __device__ __forceinline__ uint16_t key16_to_bits(uint16_t key) {
@@ -60,6 +63,7 @@ struct F16Traits<__nv_bfloat16> {
     static __device__ __forceinline__ float to_float(uint16_t b) {
         return __uint_as_float(((uint32_t)b) << 16);
     }
+    static constexpr uint16_t kInfBits = 0x7F80u;
 };
 template <>
 struct F16Traits<__half> {
@@ -73,6 +77,7 @@ struct F16Traits<__half> {
     static __device__ __forceinline__ float to_float(uint16_t b) {
         return __half2float(__ushort_as_half(b));
     }
+    static constexpr uint16_t kInfBits = 0x7C00u;
 };
 
 // ---- cache-hinted 128-bit global accesses ---------------------------------------------------
@@ -210,7 +215,7 @@ __device__ __forceinline__ void flush_tile_keys(const uint16_t* skeys, const uin
 // ---- launchers implemented in the .cu files (host, C++ linkage) -------------------------------
 cudaError_t launch_knorm_score(const Dims& d, int dtype, const void* K, const Workspace& ws,
                                void* scores_out, bool want_keys, cudaStream_t st);
-cudaError_t launch_keys_from_scores(const Dims& d, const void* scores, int64_t sb, int64_t sh,
+cudaError_t launch_keys_from_scores(const Dims& d, int dtype, const void* scores, int64_t sb, int64_t sh,
                                     const Workspace& ws, cudaStream_t st);
 cudaError_t launch_select_compact(const Dims& d, const void* K, const void* V, void* K_out,
                                   void* V_out, int32_t* idx_out, const Workspace& ws,

@@ -66,7 +66,7 @@ knorm_score_kernel(const T* __restrict__ K, Strides3 ks, int H, int S, int D, Wo
                 // -sqrt(ss) rounded once to the storage dtype (negation is exact)
                 const uint16_t bits = F16Traits<T>::from_float(sqrtf(ss)) ^ 0x8000u;
                 sscores[sl] = bits;
-                skeys[sl] = ordered_key16(bits);
+                skeys[sl] = ordered_key16(bits, F16Traits<T>::kInfBits);
             }
         }
     }
@@ -111,7 +111,7 @@ cudaError_t launch_knorm_score(const Dims& d, int dtype, const void* K, const Wo
 // ---- caller-supplied scores -> keys + histogram ------------------------------------------------
 __global__ void __launch_bounds__(kTileThreads)
 keys_from_scores_kernel(const uint16_t* __restrict__ scores, int64_t sb, int64_t sh, int H, int S,
-                        Workspace ws) {
+                        uint16_t inf_bits, Workspace ws) {
     __shared__ uint16_t skeys[kTile];
     __shared__ uint32_t shist[256];
     const int tile = blockIdx.x, row = blockIdx.y, tid = threadIdx.x;
@@ -121,17 +121,18 @@ keys_from_scores_kernel(const uint16_t* __restrict__ scores, int64_t sb, int64_t
     const int s0 = tile * kTile + tid * 4;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-        skeys[tid * 4 + i] = (s0 + i < S) ? ordered_key16(src[s0 + i]) : (uint16_t)0;
+        skeys[tid * 4 + i] = (s0 + i < S) ? ordered_key16(src[s0 + i], inf_bits) : (uint16_t)0;
     __syncthreads();
     flush_tile_keys(skeys, nullptr, shist, row, tile, S, ws, nullptr);
 }
 
-cudaError_t launch_keys_from_scores(const Dims& d, const void* scores, int64_t sb, int64_t sh,
+cudaError_t launch_keys_from_scores(const Dims& d, int dtype, const void* scores, int64_t sb, int64_t sh,
                                     const Workspace& ws, cudaStream_t st) {
     const int n_tiles = (d.S + kTile - 1) / kTile;
     dim3 grid(n_tiles, d.R);
     keys_from_scores_kernel<<<grid, kTileThreads, 0, st>>>(static_cast<const uint16_t*>(scores),
-                                                           sb, sh, d.H, d.S, ws);
+                                                           sb, sh, d.H, d.S,
+                                                           dtype == KVP_BF16 ? 0x7F80u : 0x7C00u, ws);
     return cudaPeekAtLastError();
 }
 

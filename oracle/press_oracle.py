@@ -53,11 +53,13 @@ def select_lowest_index_ties(scores: torch.Tensor, n_kept: int) -> torch.Tensor:
     """The kernels' deterministic selection rule: the n_kept largest scores, ties at the threshold
     resolved towards the LOWEST position; returned ascending. (torch.topk leaves ties unspecified,
     so this is the canonical member of the set of valid answers.)  -0.0 == +0.0, NaN is largest."""
-    B, H, S = scores.shape
     s = scores.float()
-    s = torch.where(torch.isnan(s), torch.full_like(s, float("inf")), s)
+    s = torch.where(s == 0, torch.zeros_like(s), s)  # -0.0 -> +0.0
+    bits = s.contiguous().view(torch.int32).to(torch.int64)
+    key = torch.where(bits < 0, -(bits & 0x7FFFFFFF), bits)  # monotone in the float value
+    key = torch.where(torch.isnan(s), torch.full_like(key, 2 ** 40), key)  # NaN above +inf (torch.topk order)
     # stable descending sort keeps equal scores in ascending position order
-    order = torch.sort(s, dim=-1, descending=True, stable=True).indices
+    order = torch.sort(key, dim=-1, descending=True, stable=True).indices
     return torch.sort(order[..., :n_kept], dim=-1).values
 
 
