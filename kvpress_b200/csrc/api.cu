@@ -49,7 +49,7 @@ static int validate(const kvp_problem* p, Dims* d, bool need_kv_strides = true) 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 struct WsLayout {
-    size_t keys_off, hist_off, sfx_off, scorer_off, total;
+    size_t keys_off, hist_off, sfx_off, meta_off, prefix_off, scorer_off, total;
     int S_pad, n_tiles;
     size_t hist_bytes, scorer_bytes;
 };
@@ -60,12 +60,16 @@ static WsLayout layout(const Dims& d, int scorer, int window) {
     L.S_pad = L.n_tiles * kTile;
     size_t off = 0;
     L.hist_off = off;  // hist_hi then hist_lo, zeroed together by one memset node
-    L.hist_bytes = (size_t)d.R * 256 * sizeof(uint32_t) * 2;
+    L.hist_bytes = ((size_t)d.R * 256 * 2 + (size_t)d.R * 2 + 64) * sizeof(uint32_t);
     off = align_up(off + L.hist_bytes, 256);
     L.keys_off = off;
     off = align_up(off + (size_t)d.R * L.S_pad * sizeof(uint16_t), 256);
     L.sfx_off = off;
     off = align_up(off + (size_t)d.R * L.n_tiles * kSfxStride * sizeof(uint16_t), 256);
+    L.meta_off = off;
+    off = align_up(off + (size_t)d.R * sizeof(uint2), 256);
+    L.prefix_off = off;
+    off = align_up(off + (size_t)d.R * L.n_tiles * sizeof(uint2), 256);
     L.scorer_off = off;
     L.scorer_bytes = 0;
     if (scorer == KVP_SCORER_SNAPKV) L.scorer_bytes = snapkv_scratch_bytes(d, window);
@@ -84,8 +88,12 @@ static int carve(const Dims& d, int scorer, int window, void* workspace, size_t 
     char* base = static_cast<char*>(workspace);
     ws->hist_hi = reinterpret_cast<uint32_t*>(base + L.hist_off);
     ws->hist_lo = ws->hist_hi + (size_t)d.R * 256;
+    ws->counters = ws->hist_lo + (size_t)d.R * 256;
     ws->keys = reinterpret_cast<uint16_t*>(base + L.keys_off);
     ws->tile_sfx = reinterpret_cast<uint16_t*>(base + L.sfx_off);
+    ws->row_meta = reinterpret_cast<uint2*>(base + L.meta_off);
+    ws->tile_prefix = reinterpret_cast<uint2*>(base + L.prefix_off);
+    ws->R = d.R;
     ws->scorer = base + L.scorer_off;
     ws->scorer_bytes = L.scorer_bytes;
     ws->S_pad = L.S_pad;
@@ -140,7 +148,7 @@ int kvp_launches_per_compress(const kvp_problem* p, int scorer, int* launches_ou
     switch (scorer) {
         case KVP_SCORER_STREAMING: *launches_out = 1; break;
         case KVP_SCORER_GENERIC:
-        case KVP_SCORER_KNORM: *launches_out = 4; break;  // memset, score, refine, compact
+        case KVP_SCORER_KNORM: *launches_out = 3; break;  // memset, score, select+compact
         case KVP_SCORER_SNAPKV: *launches_out = 6; break;
         case KVP_SCORER_EXPECTED_ATTENTION: *launches_out = 6; break;
         default: return KVP_ERR_BAD_ARGUMENT;

@@ -11,8 +11,8 @@
 namespace kvp {
 
 // ---- tiling of the sequence axis for the select / compact stages --------------------------
-constexpr int kTile = 1024;         // positions per tile (one CTA of kTileThreads)
-constexpr int kTileThreads = 256;   // 4 positions per thread
+constexpr int kTile = 256;          // positions per select/compact tile (one per thread)
+constexpr int kTileThreads = 256;
 constexpr int kSfxStride = 264;     // u16 per tile record: sfx[0..256], gt_hi at [257], padding
 constexpr uint16_t kForcedKey = 0xFFFFu;  // ordered key of a forced-keep position
 
@@ -26,6 +26,11 @@ struct Workspace {
     uint32_t* hist_hi;   // [R][256]   histogram of key >> 8
     uint32_t* hist_lo;   // [R][256]   histogram of key & 255 among keys with hi == threshold bin
     uint16_t* tile_sfx;  // [R][n_tiles][kSfxStride]
+    uint32_t* counters;  // [0] work-queue ticket, [1 + row] refine items done, [1 + R + row] row ready;
+                         // zeroed together with the histograms
+    uint2* row_meta;     // [R] {threshold key T, ties to take}
+    uint2* tile_prefix;  // [R][n_tiles] {kept (> T), tied (== T)} positions in the tiles before
+    int R;
     void* scorer;        // scorer-specific scratch (SnapKV / ExpectedAttention)
     size_t scorer_bytes;
     int S_pad;
@@ -155,56 +160,44 @@ __device__ __forceinline__ void warp_suffix_find(const uint32_t* hist, uint32_t 
     above = __shfl_sync(0xFFFFFFFFu, my_above, first);
 }
 
-// Adds the histogram of the high byte of `nkeys` (<= 4) keys per thread to hist (shared), using
-// warp match-aggregation so heavily tied scores (bf16 norms take ~100 distinct values) do not
-// serialise on one shared-memory address. Must be called by all 32 lanes of a warp.
-__device__ __forceinline__ void hist_add_hi(uint32_t* hist, const uint16_t* k, const bool* valid,
-                                            int n, int lane) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (i < n) {
-            const unsigned bin = valid[i] ? (unsigned)(k[i] >> 8) : 256u;
-            const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
-            if (bin < 256u && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
-        }
-    }
-}
-
-// Common tail of every score kernel: keys (and optionally scores) staged in shared memory for
-// one tile -> coalesced global writes + row histogram. skeys/sscores hold kTile entries.
-__device__ __forceinline__ void flush_tile_keys(const uint16_t* skeys, const uint16_t* sscores,
-                                                uint32_t* shist, int row, int tile, int S,
-                                                const Workspace& ws, uint16_t* scores_out) {
+// Common tail of every score kernel: KPT keys (and optionally scores) per thread staged in shared
+// memory for a chunk of KPT*blockDim positions starting at s_begin -> coalesced global writes + row
+// histogram of (key >> 8). Shared-memory atomics are warp-aggregated with match.any so heavily tied
+// scores (bf16 norms take ~100 distinct values) do not serialise on one address.
+// Call with all threads of a 256-thread CTA after a __syncthreads(); shist must be zeroed.
+template <int KPT>
+__device__ __forceinline__ void flush_chunk_keys(const uint16_t* skeys, const uint16_t* sscores,
+                                                 uint32_t* shist, int row, int s_begin, int S,
+                                                 const Workspace& ws, uint16_t* scores_out) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int s0 = tile * kTile + tid * 4;
-    uint16_t k[4];
-    bool valid[4];
+    const int s0 = s_begin + tid * KPT;
+    uint16_t k[KPT];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        k[i] = skeys[tid * 4 + i];
-        valid[i] = (s0 + i) < S;
-        if (!valid[i]) k[i] = 0;
+    for (int i = 0; i < KPT; ++i) k[i] = ((s0 + i) < S) ? skeys[tid * KPT + i] : (uint16_t)0;
+    // the keys buffer is padded to a multiple of kTile per row: unconditional vector store
+    uint16_t* kdst = ws.keys + (size_t)row * ws.S_pad + s0;
+    if (KPT == 4) {
+        uint2 pk;
+        pk.x = (uint32_t)k[0] | ((uint32_t)k[1 % KPT] << 16);
+        pk.y = (uint32_t)k[2 % KPT] | ((uint32_t)k[3 % KPT] << 16);
+        *reinterpret_cast<uint2*>(kdst) = pk;
+    } else {
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) kdst[i] = k[i];
     }
-    // keys buffer is padded to a multiple of kTile per row: unconditional 8-byte store
-    uint2 packed;
-    packed.x = (uint32_t)k[0] | ((uint32_t)k[1] << 16);
-    packed.y = (uint32_t)k[2] | ((uint32_t)k[3] << 16);
-    *reinterpret_cast<uint2*>(ws.keys + (size_t)row * ws.S_pad + s0) = packed;
     if (scores_out != nullptr) {
         uint16_t* dst = scores_out + (size_t)row * S + s0;
-        if (s0 + 3 < S && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
-            uint2 sp;
-            sp.x = (uint32_t)sscores[tid * 4] | ((uint32_t)sscores[tid * 4 + 1] << 16);
-            sp.y = (uint32_t)sscores[tid * 4 + 2] | ((uint32_t)sscores[tid * 4 + 3] << 16);
-            *reinterpret_cast<uint2*>(dst) = sp;
-        } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (valid[i]) dst[i] = sscores[tid * 4 + i];
-        }
+        for (int i = 0; i < KPT; ++i)
+            if (s0 + i < S) dst[i] = sscores[tid * KPT + i];
     }
-    hist_add_hi(shist, k, valid, 4, lane);
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+        const unsigned bin = ((s0 + i) < S) ? (unsigned)(k[i] >> 8) : 256u;
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
+        if (bin < 256u && lane == (__ffs(peers) - 1)) atomicAdd(&shist[bin], __popc(peers));
+    }
     __syncthreads();
     if (tid < 256) {
         const uint32_t c = shist[tid];

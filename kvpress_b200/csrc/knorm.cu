@@ -10,33 +10,34 @@
 
 namespace kvp {
 
+constexpr int kScoreChunk = 256;  // positions per score CTA (finer than kTile: better balance)
+
 template <typename T, int LPR>
 __global__ void __launch_bounds__(kTileThreads)
 knorm_score_kernel(const T* __restrict__ K, Strides3 ks, int H, int S, int D, Workspace ws,
                    uint16_t* __restrict__ scores_out, int want_keys) {
-    __shared__ uint16_t skeys[kTile];
-    __shared__ uint16_t sscores[kTile];
+    __shared__ uint16_t skeys[kScoreChunk];
+    __shared__ uint16_t sscores[kScoreChunk];
     __shared__ uint32_t shist[256];
 
-    const int tile = blockIdx.x;
+    const int chunk = blockIdx.x;
     const int row = blockIdx.y;
     const int b = row / H, h = row % H;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     shist[tid] = 0;  // kTileThreads == 256
 
-    constexpr int RPW = 32 / LPR;              // rows per warp-wide load
-    constexpr int TOK_PER_WARP = kTile / (kTileThreads / 32);  // 128
+    constexpr int RPW = 32 / LPR;                                   // rows per warp-wide load
+    constexpr int TOK_PER_WARP = kScoreChunk / (kTileThreads / 32);  // 32
     constexpr int ITERS = TOK_PER_WARP / RPW;
-    constexpr int U = 8;                       // independent 16-byte loads in flight per lane
+    constexpr int U = (ITERS < 8) ? ITERS : 8;  // independent 16-byte loads in flight per lane
     static_assert(ITERS % U == 0, "unroll must divide the iteration count");
 
-    const int sub = lane % LPR;        // which 16-byte chunk of the row
-    const int rsel = lane / LPR;       // which row of the RPW rows
-    const int nvec = D >> 3;           // 16-byte chunks per row
+    const int sub = lane % LPR;   // which 16-byte piece of the row
+    const int rsel = lane / LPR;  // which row of the RPW rows
+    const int nvec = D >> 3;      // 16-byte pieces per row
     const T* base = K + (int64_t)b * ks.b + (int64_t)h * ks.h + (int64_t)sub * 8;
-    const int s_warp = tile * kTile + warp * TOK_PER_WARP;
-    const uint64_t pol_keep = l2_policy_evict_last();
+    const int s_warp = chunk * kScoreChunk + warp * TOK_PER_WARP;
 
 #pragma unroll 1
     for (int it = 0; it < ITERS; it += U) {
@@ -45,7 +46,7 @@ knorm_score_kernel(const T* __restrict__ K, Strides3 ks, int H, int S, int D, Wo
         for (int u = 0; u < U; ++u) {
             const int s = s_warp + (it + u) * RPW + rsel;
             v[u] = make_int4(0, 0, 0, 0);
-            if (s < S && sub < nvec) v[u] = ldg_hint(base + (int64_t)s * ks.s, pol_keep);
+            if (s < S && sub < nvec) v[u] = ldg_plain(base + (int64_t)s * ks.s);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -71,22 +72,18 @@ knorm_score_kernel(const T* __restrict__ K, Strides3 ks, int H, int S, int D, Wo
         }
     }
     __syncthreads();
+    const int s_begin = chunk * kScoreChunk;
     if (want_keys) {
-        flush_tile_keys(skeys, sscores, shist, row, tile, S, ws, scores_out);
-    } else {
-        // score-only call: just write the scores
-        const int s0 = tile * kTile + tid * 4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (s0 + i < S) scores_out[(size_t)row * S + s0 + i] = sscores[tid * 4 + i];
+        flush_chunk_keys<1>(skeys, sscores, shist, row, s_begin, S, ws, scores_out);
+    } else if (s_begin + tid < S) {  // score-only call
+        scores_out[(size_t)row * S + s_begin + tid] = sscores[tid];
     }
 }
 
 template <typename T>
 static cudaError_t launch_knorm_t(const Dims& d, const void* K, const Workspace& ws,
                                   void* scores_out, bool want_keys, cudaStream_t st) {
-    const int n_tiles = (d.S + kTile - 1) / kTile;
-    dim3 grid(n_tiles, d.R);
+    dim3 grid((d.S + kScoreChunk - 1) / kScoreChunk, d.R);
     const int nvec = d.D / 8;
     const T* Kp = static_cast<const T*>(K);
     uint16_t* so = static_cast<uint16_t*>(scores_out);
@@ -118,12 +115,10 @@ keys_from_scores_kernel(const uint16_t* __restrict__ scores, int64_t sb, int64_t
     const int b = row / H, h = row % H;
     shist[tid] = 0;
     const uint16_t* src = scores + (int64_t)b * sb + (int64_t)h * sh;
-    const int s0 = tile * kTile + tid * 4;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        skeys[tid * 4 + i] = (s0 + i < S) ? ordered_key16(src[s0 + i], inf_bits) : (uint16_t)0;
+    const int s = tile * kTile + tid;
+    skeys[tid] = (s < S) ? ordered_key16(src[s], inf_bits) : (uint16_t)0;
     __syncthreads();
-    flush_tile_keys(skeys, nullptr, shist, row, tile, S, ws, nullptr);
+    flush_chunk_keys<1>(skeys, nullptr, shist, row, tile * kTile, S, ws, nullptr);
 }
 
 cudaError_t launch_keys_from_scores(const Dims& d, int dtype, const void* scores, int64_t sb, int64_t sh,

@@ -3,248 +3,349 @@
 // Replaces scores.topk(n_kept).indices + keys.gather + values.gather
 // (kvpress/presses/scorer_press.py:95-100) for 16-bit scores:
 //   * the score stage left, per (b,h) row, the ordered keys and a 256-bin histogram of key>>8;
-//   * refine_kernel  : every tile finds the threshold bin b1 from that histogram, histograms the
-//                      low byte of the keys that fall in b1 (-> row hist_lo) and records, per
-//                      tile, the suffix counts of those low bytes + the count of keys above b1;
-//   * compact_kernel : every tile derives the exact 16-bit threshold T and the number of ties to
-//                      take, sums the records of the tiles before it (no ordering constraint
-//                      between CTAs), ranks its own 1024 positions with one block scan and copies
-//                      the kept K and V rows (16-byte vectors, 8 in flight per thread) to
-//                      [B,H,n_kept,D] in ascending position order. Ties at T go to the lowest
-//                      positions.
+// ONE persistent kernel (select_compact_kernel) pulls two kinds of items from a ticket counter:
+//   * refine item  : (row, 8 tiles) finds the threshold bin b1 from that histogram, histograms the
+//                    low byte of the keys that fall in b1 (-> row hist_lo, one warp per tile) and
+//                    records, per tile, the suffix counts of those low bytes + the count of keys
+//                    above b1; then bumps the row's "refined" counter;
+//   * compact item : (row, tile) waits for the row's counter, derives the exact 16-bit threshold T
+//                    and the number of ties to take, sums the records of the tiles before it, ranks
+//                    its own 1024 positions with one block scan and copies the kept K and V rows
+//                    (16-byte vectors, 8 in flight per thread) to [B,H,n_kept,D] in ascending
+//                    position order. Ties at T go to the lowest positions.
 // Tiles are visited in REVERSE order of the score stage so the K rows touched last (still in the
 // 126 MB L2) are re-read first.
 #include "common.cuh"
 
 namespace kvp {
 
-__global__ void __launch_bounds__(kTileThreads)
-refine_kernel(int S, int n_kept, Workspace ws) {
-    __shared__ uint32_t shist[256];
-    __shared__ uint32_t slo[260];
-    __shared__ uint32_t swarp[8];
-    __shared__ int s_b1;
+constexpr int kTilesPerWarp = 4;                                  // refine: tiles per warp
+constexpr int kGroupTiles = (kTileThreads / 32) * kTilesPerWarp;  // tiles per refine item (32)
 
-    const int tile = blockIdx.x, row = blockIdx.y, tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-
-    shist[tid] = ws.hist_hi[(size_t)row * 256 + tid];
-    slo[tid] = 0;
-    if (tid < 4) slo[256 + tid] = 0;
-    // issue the key load before the barrier so it overlaps the histogram read
-    const int s0 = tile * kTile + tid * 4;
-    const uint2 packed =
-        *reinterpret_cast<const uint2*>(ws.keys + (size_t)row * ws.S_pad + s0);
-    __syncthreads();
-    if (warp == 0) {
-        int b1;
-        uint32_t above;
-        warp_suffix_find(shist, (uint32_t)n_kept, lane, b1, above);
-        if (lane == 0) s_b1 = b1;
-    }
-    __syncthreads();
-    const unsigned b1 = (unsigned)s_b1;
-
-    const uint16_t k[4] = {(uint16_t)(packed.x & 0xFFFF), (uint16_t)(packed.x >> 16),
-                           (uint16_t)(packed.y & 0xFFFF), (uint16_t)(packed.y >> 16)};
-    uint32_t n_gt = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool valid = (s0 + i) < S;
-        const unsigned hi = k[i] >> 8;
-        n_gt += (valid && hi > b1) ? 1u : 0u;
-        const unsigned bin = (valid && hi == b1) ? (unsigned)(k[i] & 0xFF) : 256u;
-        const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
-        if (bin < 256u && lane == (__ffs(peers) - 1)) atomicAdd(&slo[bin], __popc(peers));
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) n_gt += __shfl_xor_sync(0xFFFFFFFFu, n_gt, off);
-    if (lane == 0) swarp[warp] = n_gt;
-    __syncthreads();
-
-    // row-level low-byte histogram
-    const uint32_t c = slo[tid];
-    if (c) atomicAdd(&ws.hist_lo[(size_t)row * 256 + tid], c);
-
-    // per-tile suffix sums sfx[j] = #candidates with low byte >= j  (block-wide suffix scan)
-    uint32_t v = c;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t t = __shfl_down_sync(0xFFFFFFFFu, v, off);
-        if (lane + off < 32) v += t;
-    }
-    __shared__ uint32_t swsum[8];
-    if (lane == 0) swsum[warp] = v;  // total of this warp's 32 bins
-    __syncthreads();
-    uint32_t tail = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) tail += (w > warp) ? swsum[w] : 0u;
-    uint16_t* rec = ws.tile_sfx + ((size_t)row * ws.n_tiles + tile) * kSfxStride;
-    rec[tid] = (uint16_t)(v + tail);
-    if (tid == 0) {
-        uint32_t g = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) g += swarp[w];
-        rec[256] = 0;
-        rec[257] = (uint16_t)g;
-    }
-}
-
-// Copies `count` rows of `nvec` 16-byte vectors: dst row j <- src row list[j].
-template <bool kKeepInL2>
-__device__ __forceinline__ void copy_rows(const char* __restrict__ src, int64_t src_row_bytes,
-                                          char* __restrict__ dst, int64_t dst_row_bytes,
-                                          const int* __restrict__ list, int count, int nvec) {
+// Copies `count` rows of `nvec` 16-byte vectors of BOTH tensors: dst row j <- src row list[j].
+// K rows are plain loads (they may still sit in L2 from the score stage), V rows and all stores are
+// streamed (evict-first). 2*U independent 16-byte loads are in flight per thread.
+__device__ __forceinline__ void copy_rows_kv(const char* __restrict__ srcK, int64_t k_row_bytes,
+                                             const char* __restrict__ srcV, int64_t v_row_bytes,
+                                             char* __restrict__ dstK, char* __restrict__ dstV,
+                                             int64_t dst_row_bytes, const int* __restrict__ list,
+                                             int count, int nvec) {
     constexpr int U = 4;
     const int total = count * nvec;
     const uint64_t pol_first = l2_policy_evict_first();
     for (int base = threadIdx.x; base < total; base += kTileThreads * U) {
-        int4 v[U];
-        int rr[U], cc[U];
+        int4 vk[U], vv[U];
+        int64_t doff[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int i = base + u * kTileThreads;
-            rr[u] = -1;
+            doff[u] = -1;
             if (i < total) {
-                rr[u] = i / nvec;
-                cc[u] = i - rr[u] * nvec;
-                const char* p = src + (int64_t)list[rr[u]] * src_row_bytes + cc[u] * 16;
-                v[u] = kKeepInL2 ? ldg_plain(p) : ldg_hint(p, pol_first);
+                const int r = i / nvec;
+                const int cc = i - r * nvec;
+                const int64_t src_row = list[r];
+                doff[u] = (int64_t)r * dst_row_bytes + cc * 16;
+                vk[u] = ldg_plain(srcK + src_row * k_row_bytes + cc * 16);
+                vv[u] = ldg_hint(srcV + src_row * v_row_bytes + cc * 16, pol_first);
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (rr[u] >= 0)
-                stg_hint(dst + (int64_t)rr[u] * dst_row_bytes + cc[u] * 16, v[u], pol_first);
+            if (doff[u] >= 0) {
+                stg_hint(dstK + doff[u], vk[u], pol_first);
+                stg_hint(dstV + doff[u], vv[u], pol_first);
+            }
     }
 }
 
-__global__ void __launch_bounds__(kTileThreads)
-compact_kernel(const char* __restrict__ K, const char* __restrict__ V, Strides3 ks, Strides3 vs,
-               char* __restrict__ K_out, char* __restrict__ V_out, int32_t* __restrict__ idx_out,
-               int H, int S, int D, int n_kept, Workspace ws) {
-    __shared__ uint32_t shist[256];
-    __shared__ uint32_t slo[256];
-    __shared__ int s_list[kTile];
-    __shared__ uint32_t s_scan[8];
-    __shared__ uint32_t s_red[2][8];
-    __shared__ uint32_t s_thr[3];  // T, n_take, lo1
+struct SelectSmem {
+    uint32_t hist[256];                    // hist_hi of the current row
+    uint32_t lo[kTileThreads / 32][256];   // refine: per-warp low-byte histograms; scan: lo[0] = hist_lo
+    int list[kTile];
+    uint32_t wsum[2][8];
+    uint32_t thr[3];
+    int item;
+    int b1;
+    int last;
+};
 
-    // reverse visiting order: last rows / last tiles of the score stage first
-    const int tile = (int)gridDim.x - 1 - (int)blockIdx.x;
-    const int row = (int)gridDim.y - 1 - (int)blockIdx.y;
+// Row scan, executed by the CTA that finished the LAST refine item of a row: exact threshold T,
+// number of ties to take, and for every tile the number of kept (> T) and tied (== T) positions in
+// the tiles before it. Publishes row_meta / tile_prefix, then raises the row's ready flag.
+__device__ __forceinline__ void scan_row(SelectSmem& sm, int row, int n_kept, const Workspace& ws) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = row / H, h = row % H;
-
-    shist[tid] = ws.hist_hi[(size_t)row * 256 + tid];
-    slo[tid] = ws.hist_lo[(size_t)row * 256 + tid];
-    const int s0 = tile * kTile + tid * 4;
-    const uint2 packed =
-        *reinterpret_cast<const uint2*>(ws.keys + (size_t)row * ws.S_pad + s0);
+    __syncthreads();
+    sm.lo[0][tid] = __ldcg(&ws.hist_lo[(size_t)row * 256 + tid]);  // sm.hist still holds hist_hi
     __syncthreads();
     if (warp == 0) {
         int b1, lo1;
         uint32_t above1, above2;
-        warp_suffix_find(shist, (uint32_t)n_kept, lane, b1, above1);
+        warp_suffix_find(sm.hist, (uint32_t)n_kept, lane, b1, above1);
         const uint32_t need1 = (uint32_t)n_kept - above1;  // >= 1
-        warp_suffix_find(slo, need1, lane, lo1, above2);
+        warp_suffix_find(sm.lo[0], need1, lane, lo1, above2);
         if (lane == 0) {
-            s_thr[0] = ((uint32_t)b1 << 8) | (uint32_t)lo1;
-            s_thr[1] = need1 - above2;  // ties (key == T) to take, >= 1
-            s_thr[2] = (uint32_t)lo1;
+            sm.thr[0] = ((uint32_t)b1 << 8) | (uint32_t)lo1;
+            sm.thr[1] = need1 - above2;  // ties (key == T) to take, >= 1
+            sm.thr[2] = (uint32_t)lo1;
         }
     }
     __syncthreads();
-    const uint32_t T = s_thr[0], n_take = s_thr[1], lo1 = s_thr[2];
-
-    // ---- kept / tie counts of the tiles before this one -----------------------------------
-    uint32_t gt_before = 0, eq_before = 0;
-    {
-        const uint16_t* recs = ws.tile_sfx + (size_t)row * ws.n_tiles * kSfxStride;
-        for (int t = tid; t < tile; t += kTileThreads) {
+    const uint32_t lo1 = sm.thr[2];
+    const uint16_t* recs = ws.tile_sfx + (size_t)row * ws.n_tiles * kSfxStride;
+    uint2* prefix = ws.tile_prefix + (size_t)row * ws.n_tiles;
+    uint32_t carry_gt = 0, carry_eq = 0;
+    for (int t0 = 0; t0 < ws.n_tiles; t0 += kTileThreads) {
+        const int t = t0 + tid;
+        uint32_t gt = 0, eq = 0;
+        if (t < ws.n_tiles) {
             const uint16_t* r = recs + (size_t)t * kSfxStride;
-            const uint32_t ge = r[lo1], gt = r[lo1 + 1];
-            gt_before += (uint32_t)r[257] + gt;
-            eq_before += ge - gt;
+            const uint32_t ge = __ldcg(r + lo1), g2 = __ldcg(r + lo1 + 1);
+            gt = (uint32_t)__ldcg(r + 257) + g2;
+            eq = ge - g2;
         }
+        uint32_t igt = gt, ieq = eq;  // inclusive warp scans
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            gt_before += __shfl_xor_sync(0xFFFFFFFFu, gt_before, off);
-            eq_before += __shfl_xor_sync(0xFFFFFFFFu, eq_before, off);
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, igt, off);
+            const uint32_t b = __shfl_up_sync(0xFFFFFFFFu, ieq, off);
+            if (lane >= off) {
+                igt += a;
+                ieq += b;
+            }
         }
-        if (lane == 0) {
-            s_red[0][warp] = gt_before;
-            s_red[1][warp] = eq_before;
+        __syncthreads();
+        if (lane == 31) {
+            sm.wsum[0][warp] = igt;
+            sm.wsum[1][warp] = ieq;
         }
-    }
-
-    // ---- rank this tile's positions: packed scan, low 16 bits = #gt, high 16 bits = #eq --------
-    const uint16_t k[4] = {(uint16_t)(packed.x & 0xFFFF), (uint16_t)(packed.x >> 16),
-                           (uint16_t)(packed.y & 0xFFFF), (uint16_t)(packed.y >> 16)};
-    uint32_t f[4];
-    uint32_t tsum = 0;
+        __syncthreads();
+        uint32_t pg = carry_gt, pe = carry_eq, tg = 0, te = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool valid = (s0 + i) < S;
-        f[i] = valid ? ((k[i] > T) ? 1u : ((k[i] == T) ? 0x10000u : 0u)) : 0u;
-        tsum += f[i];
+        for (int w = 0; w < 8; ++w) {
+            pg += (w < warp) ? sm.wsum[0][w] : 0u;
+            pe += (w < warp) ? sm.wsum[1][w] : 0u;
+            tg += sm.wsum[0][w];
+            te += sm.wsum[1][w];
+        }
+        if (t < ws.n_tiles) prefix[t] = make_uint2(pg + igt - gt, pe + ieq - eq);
+        carry_gt += tg;
+        carry_eq += te;
     }
-    uint32_t incl = tsum;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-        if (lane >= off) incl += t;
+    if (tid == 0) {
+        ws.row_meta[row] = make_uint2(sm.thr[0], sm.thr[1]);
     }
-    if (lane == 31) s_scan[warp] = incl;
+    __threadfence();
     __syncthreads();
-    uint32_t wprefix = 0, total = 0;
-    gt_before = 0;
-    eq_before = 0;
+    if (tid == 0) atomicExch(&ws.counters[1 + ws.R + row], 1u);
+}
+
+// ---- refine item: (row, group of kGroupTiles tiles); one warp per tile, no block barriers inside ----
+__device__ __forceinline__ void refine_item(SelectSmem& sm, int row, int group, int n_groups, int S,
+                                            int n_kept, const Workspace& ws) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    sm.hist[tid] = ws.hist_hi[(size_t)row * 256 + tid];
+    __syncthreads();
+    if (warp == 0) {
+        int b1;
+        uint32_t above;
+        warp_suffix_find(sm.hist, (uint32_t)n_kept, lane, b1, above);
+        if (lane == 0) sm.b1 = b1;
+    }
+    __syncthreads();
+    const unsigned b1 = (unsigned)sm.b1;
+    uint32_t* lo = sm.lo[warp];
+    uint32_t acc[8];  // group-level low-byte histogram, bins [8*lane, 8*lane+8) of this warp's tiles
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0;
+#pragma unroll 1
+    for (int tw = 0; tw < kTilesPerWarp; ++tw) {
+        const int tile = group * kGroupTiles + warp * kTilesPerWarp + tw;
+        if (tile >= ws.n_tiles) break;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lo[lane * 8 + i] = 0;
+        __syncwarp();
+        // kTile == 256 keys: one 16-byte load per lane
+        const int4 v = *reinterpret_cast<const int4*>(ws.keys + (size_t)row * ws.S_pad +
+                                                      (size_t)tile * kTile + lane * 8);
+        const uint32_t w4[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+        uint32_t n_gt = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const unsigned k = (w4[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu;
+            const bool valid = (tile * kTile + lane * 8 + q) < S;
+            const unsigned hi = k >> 8;
+            n_gt += (valid && hi > b1) ? 1u : 0u;
+            if (valid && hi == b1) atomicAdd(&lo[k & 0xFF], 1u);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) n_gt += __shfl_xor_sync(0xFFFFFFFFu, n_gt, off);
+        __syncwarp();
+        // suffix sums over the 256 bins: lane owns bins [8*lane, 8*lane+8)
+        uint32_t c[8], lane_sum = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            c[i] = lo[lane * 8 + i];
+            lane_sum += c[i];
+            acc[i] += c[i];
+        }
+        uint32_t sfx = lane_sum;  // inclusive suffix over lanes
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_down_sync(0xFFFFFFFFu, sfx, off);
+            if (lane + off < 32) sfx += t;
+        }
+        uint32_t run = sfx - lane_sum;  // candidates in bins above this lane's
+        uint32_t out[8];
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+            run += c[i];
+            out[i] = run;
+        }
+        uint16_t* rec = ws.tile_sfx + ((size_t)row * ws.n_tiles + tile) * kSfxStride;
+        uint4 pk;
+        pk.x = out[0] | (out[1] << 16);
+        pk.y = out[2] | (out[3] << 16);
+        pk.z = out[4] | (out[5] << 16);
+        pk.w = out[6] | (out[7] << 16);
+        *reinterpret_cast<uint4*>(rec + lane * 8) = pk;
+        if (lane == 0) {
+            rec[256] = 0;
+            rec[257] = (uint16_t)n_gt;
+        }
+        __syncwarp();
+    }
+    // warp's share of the row's low-byte histogram
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (acc[i]) atomicAdd(&ws.hist_lo[(size_t)row * 256 + lane * 8 + i], acc[i]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sm.last = (atomicAdd(&ws.counters[1 + row], 1u) == (uint32_t)(n_groups - 1));
+    __syncthreads();
+    if (sm.last) {
+        __threadfence();
+        scan_row(sm, row, n_kept, ws);
+    }
+}
+
+// ---- compact item: (row, tile of kTile == kTileThreads positions, one per thread) ---------------------
+__device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, const char* K,
+                                             const char* V, Strides3 ks, Strides3 vs, char* K_out,
+                                             char* V_out, int32_t* idx_out, int H, int S, int D,
+                                             int n_kept, const Workspace& ws) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = row / H, h = row % H;
+    const int s = tile * kTile + tid;
+    const uint32_t key = ws.keys[(size_t)row * ws.S_pad + s];  // independent of the refine stage
+    // wait until the row scan has published (bounded spin; traps instead of hanging the GPU)
+    if (tid == 0) {
+        const volatile uint32_t* flag = ws.counters + 1 + ws.R + row;
+        uint32_t spins = 0;
+        while (*flag == 0u) {
+            __nanosleep(64);
+            if (++spins > (1u << 24)) __trap();
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    const uint2 meta = __ldcg(&ws.row_meta[row]);
+    const uint2 before = __ldcg(&ws.tile_prefix[(size_t)row * ws.n_tiles + tile]);
+    const uint32_t T = meta.x, n_take = meta.y;
+    const uint32_t gt_before = before.x, eq_before = before.y;
+
+    const bool valid = s < S;
+    const bool is_gt = valid && key > T;
+    const bool is_eq = valid && key == T;
+    const unsigned m_gt = __ballot_sync(0xFFFFFFFFu, is_gt);
+    const unsigned m_eq = __ballot_sync(0xFFFFFFFFu, is_eq);
+    if (lane == 0) {
+        sm.wsum[0][warp] = __popc(m_gt);
+        sm.wsum[1][warp] = __popc(m_eq);
+    }
+    __syncthreads();
+    uint32_t gt_rank = __popc(m_gt & ((1u << lane) - 1u));
+    uint32_t eq_rank = __popc(m_eq & ((1u << lane) - 1u));
+    uint32_t tot_gt = 0, tot_eq = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-        wprefix += (w < warp) ? s_scan[w] : 0u;
-        total += s_scan[w];
-        gt_before += s_red[0][w];
-        eq_before += s_red[1][w];
+        gt_rank += (w < warp) ? sm.wsum[0][w] : 0u;
+        eq_rank += (w < warp) ? sm.wsum[1][w] : 0u;
+        tot_gt += sm.wsum[0][w];
+        tot_eq += sm.wsum[1][w];
     }
     // ties are taken in position order: this tile may take those with global tie rank < n_take
     const uint32_t tie_room = (n_take > eq_before) ? (n_take - eq_before) : 0u;
     const uint32_t out_base = gt_before + min(eq_before, n_take);
-    uint32_t run = wprefix + incl - tsum;  // exclusive prefix of this thread
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t gt_rank = run & 0xFFFFu, eq_rank = run >> 16;
-        const bool keep = (f[i] == 1u) || (f[i] == 0x10000u && eq_rank < tie_room);
-        if (keep) s_list[gt_rank + min(eq_rank, tie_room)] = s0 + i;
-        run += f[i];
-    }
-    const int count = (int)((total & 0xFFFFu) + min(total >> 16, tie_room));
+    if (is_gt || (is_eq && eq_rank < tie_room)) sm.list[gt_rank + min(eq_rank, tie_room)] = s;
+    const int count = (int)(tot_gt + min(tot_eq, tie_room));
     __syncthreads();
-    if (count == 0) return;
+    if (count > 0) {
+        const int64_t out_row0 = (int64_t)row * n_kept + out_base;
+        if (idx_out != nullptr && tid < count) idx_out[out_row0 + tid] = sm.list[tid];
+        const int64_t row_bytes = (int64_t)D * 2;
+        copy_rows_kv(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
+                     V + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2, vs.s * 2,
+                     K_out + out_row0 * row_bytes, V_out + out_row0 * row_bytes, row_bytes, sm.list,
+                     count, D >> 3);
+    }
+}
 
-    const int64_t out_row0 = (int64_t)row * n_kept + out_base;
-    if (idx_out != nullptr)
-        for (int j = tid; j < count; j += kTileThreads) idx_out[out_row0 + j] = s_list[j];
+// Persistent select+compact kernel: CTAs pull items from one ticket counter. Items [0, nA) are the
+// refine items (the last one to finish for a row also runs that row's scan and raises its ready
+// flag), items [nA, nA + nB) the compact items (last rows / last tiles first, so K rows the score
+// stage touched last are re-read while still in L2). A compact item only waits for refine items,
+// which precede it in the queue and never wait themselves => no deadlock for any grid size.
+__global__ void __launch_bounds__(kTileThreads, 4)
+select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, Strides3 ks,
+                      Strides3 vs, char* __restrict__ K_out, char* __restrict__ V_out,
+                      int32_t* __restrict__ idx_out, int H, int S, int D, int n_kept,
+                      Workspace ws) {
+    __shared__ SelectSmem sm;
+    const int R = ws.R;
+    const int n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
+    const int nA = R * n_groups, nB = R * ws.n_tiles;
+    while (true) {
+        __syncthreads();  // previous item's shared state is dead
+        if (threadIdx.x == 0) sm.item = (int)atomicAdd(&ws.counters[0], 1u);
+        __syncthreads();
+        const int item = sm.item;
+        if (item >= nA + nB) break;
+        if (item < nA) {
+            refine_item(sm, item / n_groups, item % n_groups, n_groups, S, n_kept, ws);
+        } else {
+            const int j = item - nA;
+            const int row = R - 1 - j / ws.n_tiles;
+            const int tile = ws.n_tiles - 1 - j % ws.n_tiles;
+            compact_item(sm, row, tile, K, V, ks, vs, K_out, V_out, idx_out, H, S, D, n_kept, ws);
+        }
+    }
+}
 
-    const int nvec = D >> 3;
-    const int64_t row_bytes = (int64_t)D * 2;
-    copy_rows<true>(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
-                    K_out + out_row0 * row_bytes, row_bytes, s_list, count, nvec);
-    copy_rows<false>(V + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2, vs.s * 2,
-                     V_out + out_row0 * row_bytes, row_bytes, s_list, count, nvec);
+static int persistent_grid(const void* kernel, int threads, int n_items) {
+    static int sm_count = 0;
+    int dev = 0;
+    if (sm_count == 0) {
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+    if (per_sm <= 0) per_sm = 1;
+    const int grid = sm_count * per_sm;
+    return n_items < grid ? n_items : grid;
 }
 
 cudaError_t launch_select_compact(const Dims& d, const void* K, const void* V, void* K_out,
                                   void* V_out, int32_t* idx_out, const Workspace& ws,
                                   cudaStream_t st) {
-    dim3 grid(ws.n_tiles, d.R);
-    refine_kernel<<<grid, kTileThreads, 0, st>>>(d.S, d.n_kept, ws);
-    cudaError_t e = cudaPeekAtLastError();
-    if (e != cudaSuccess) return e;
-    compact_kernel<<<grid, kTileThreads, 0, st>>>(
+    const int n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
+    const int n_items = d.R * n_groups + d.R * ws.n_tiles;
+    const int grid =
+        persistent_grid(reinterpret_cast<const void*>(select_compact_kernel), kTileThreads, n_items);
+    select_compact_kernel<<<grid, kTileThreads, 0, st>>>(
         static_cast<const char*>(K), static_cast<const char*>(V), d.ks, d.vs,
-        static_cast<char*>(K_out), static_cast<char*>(V_out), idx_out, d.H, d.S, d.D, d.n_kept,
-        ws);
+        static_cast<char*>(K_out), static_cast<char*>(V_out), idx_out, d.H, d.S, d.D, d.n_kept, ws);
     return cudaPeekAtLastError();
 }
 
@@ -271,12 +372,11 @@ streaming_compact_kernel(const char* __restrict__ K, const char* __restrict__ V,
     const int64_t out_row0 = (int64_t)row * n_kept + j0;
     if (idx_out != nullptr)
         for (int j = tid; j < count; j += kTileThreads) idx_out[out_row0 + j] = s_list[j];
-    const int nvec = D >> 3;
     const int64_t row_bytes = (int64_t)D * 2;
-    copy_rows<false>(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
-                     K_out + out_row0 * row_bytes, row_bytes, s_list, count, nvec);
-    copy_rows<false>(V + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2, vs.s * 2,
-                     V_out + out_row0 * row_bytes, row_bytes, s_list, count, nvec);
+    copy_rows_kv(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
+                 V + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2, vs.s * 2,
+                 K_out + out_row0 * row_bytes, V_out + out_row0 * row_bytes, row_bytes, s_list, count,
+                 D >> 3);
 }
 
 cudaError_t launch_streaming_compress(const Dims& d, int n_sink, const void* K, const void* V,
