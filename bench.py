@@ -49,7 +49,7 @@ WORKLOADS = {
     "decoding_knorm": dict(scorer="knorm", B=1, Hkv=8, Hq=8, S=2560, D=128, ratio=None, n_kept=2048,
                            config_index=3, label="DecodingPress(Knorm) steady-state compaction 2560->2048"),
 }
-DEFAULT_WORKLOAD = "knorm_128k"
+DEFAULT_WORKLOAD = "ea_128k"
 
 
 def kept_count(S: int, ratio: float) -> int:

@@ -150,7 +150,7 @@ int kvp_launches_per_compress(const kvp_problem* p, int scorer, int* launches_ou
         case KVP_SCORER_GENERIC:
         case KVP_SCORER_KNORM: *launches_out = 3; break;  // memset, score, select+compact
         case KVP_SCORER_SNAPKV: *launches_out = 6; break;
-        case KVP_SCORER_EXPECTED_ATTENTION: *launches_out = 6; break;
+        case KVP_SCORER_EXPECTED_ATTENTION: *launches_out = 4; break;  // memset, logits, finalize, select+compact
         default: return KVP_ERR_BAD_ARGUMENT;
     }
     return KVP_OK;
@@ -235,8 +235,10 @@ int kvp_snapkv_score(const kvp_problem* p, const void* K, const void* q_window, 
     Workspace ws;
     WsLayout L;
     if ((rc = carve(d, KVP_SCORER_SNAPKV, window, workspace, workspace_bytes, &ws, &L))) return rc;
-    cudaError_t e = launch_snapkv_score(d, p->dtype, K, q_window, window, kernel_size, ws,
-                                        scores_out, false, static_cast<cudaStream_t>(stream));
+    cudaError_t e = cudaMemsetAsync(ws.hist_hi, 0, L.hist_bytes, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e);
+    e = launch_snapkv_score(d, p->dtype, K, q_window, window, kernel_size, ws, scores_out, false,
+                            static_cast<cudaStream_t>(stream));
     if (e == cudaErrorNotSupported) return KVP_ERR_UNSUPPORTED_SHAPE;
     return e == cudaSuccess ? KVP_OK : fail_cuda(e);
 }
@@ -282,8 +284,10 @@ int kvp_expected_attention_score(const kvp_problem* p, const void* K, const void
     WsLayout L;
     if ((rc = carve(d, KVP_SCORER_EXPECTED_ATTENTION, 0, workspace, workspace_bytes, &ws, &L)))
         return rc;
-    cudaError_t e = launch_ea_score(d, p->dtype, K, V, mu, cov, epsilon, n_sink, use_vnorm, ws,
-                                    scores_out, false, static_cast<cudaStream_t>(stream));
+    cudaError_t e = cudaMemsetAsync(ws.hist_hi, 0, L.hist_bytes, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e);
+    e = launch_ea_score(d, p->dtype, K, V, mu, cov, epsilon, n_sink, use_vnorm, ws, scores_out, false,
+                        static_cast<cudaStream_t>(stream));
     if (e == cudaErrorNotSupported) return KVP_ERR_UNSUPPORTED_SHAPE;
     return e == cudaSuccess ? KVP_OK : fail_cuda(e);
 }

@@ -15,6 +15,10 @@ constexpr int kTile = 256;          // positions per select/compact tile (one pe
 constexpr int kTileThreads = 256;
 constexpr int kSfxStride = 264;     // u16 per tile record: sfx[0..256], gt_hi at [257], padding
 constexpr uint16_t kForcedKey = 0xFFFFu;  // ordered key of a forced-keep position
+constexpr int kScoreChunkGeneric = 256;   // positions per CTA of the plain streaming score kernels
+// counters[] layout: [0] ticket, [1, 1+R) refine done, [1+R, 1+2R) row ready, then the slot below:
+// order-preserving uint image of the largest valid score (for the reference's max+1 sentinel)
+__host__ __device__ constexpr int kCounterMaxSlot(int R) { return 1 + 2 * R; }
 
 struct Strides3 {
     int64_t b, h, s;
@@ -69,6 +73,7 @@ struct F16Traits<__nv_bfloat16> {
         return __uint_as_float(((uint32_t)b) << 16);
     }
     static constexpr uint16_t kInfBits = 0x7F80u;
+    static constexpr int kMmaFormat = 1;  // tcgen05 kind::f16 operand format: BF16
 };
 template <>
 struct F16Traits<__half> {
@@ -83,6 +88,7 @@ struct F16Traits<__half> {
         return __half2float(__ushort_as_half(b));
     }
     static constexpr uint16_t kInfBits = 0x7C00u;
+    static constexpr int kMmaFormat = 0;  // F16
 };
 
 // ---- cache-hinted 128-bit global accesses ---------------------------------------------------
@@ -224,6 +230,8 @@ cudaError_t launch_snapkv_score(const Dims& d, int dtype, const void* K, const v
                                 int window, int kernel_size, const Workspace& ws,
                                 void* scores_out, bool want_keys, cudaStream_t st);
 size_t ea_scratch_bytes(const Dims& d);
+cudaError_t launch_fill_sentinel(int dtype, void* scores_out, int R, int S, int lo, int hi,
+                                 const Workspace& ws, cudaStream_t st);
 cudaError_t launch_ea_score(const Dims& d, int dtype, const void* K, const void* V, const void* mu,
                             const void* cov, float eps, int n_sink, int use_vnorm,
                             const Workspace& ws, void* scores_out, bool want_keys,

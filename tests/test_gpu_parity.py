@@ -205,3 +205,92 @@ def test_errors_are_loud():
     kd = torch.randn(1, 2, 128, 12, dtype=torch.bfloat16, device=DEV)
     with pytest.raises(RuntimeError, match="unsupported shape"):
         nat.knorm_compress(kd, kd, 64)
+
+
+# ---------------------------------------------------------------------------------------------------
+# attention-based scorers: tolerance helpers
+# ---------------------------------------------------------------------------------------------------
+def _round_like(x32: torch.Tensor, dtype) -> torch.Tensor:
+    return x32.to(dtype)
+
+
+def _assert_scores_close(got, ref16, hi32, forced: slice, dtype):
+    """got: kernel scores (16 bit). ref16: the reference's 16-bit scores. hi32: fp32 evaluation of the
+    same formula (forced positions = +inf). Bars: <= 1 ulp from the rounded fp32 evaluation (i.e. the
+    kernel's fp32 math is within 1e-3 relative of it), and within the reference's own 16-bit rounding
+    noise (a handful of ulps) of the reference scores."""
+    S = got.shape[-1]
+    keep = torch.ones(S, dtype=torch.bool)
+    keep[forced] = False
+    g, r, h = got[..., keep], ref16[..., keep], hi32[..., keep]
+    d_hi = ulp16_diff(g, _round_like(h, dtype))
+    assert d_hi.max() <= 1, f"max ulp distance to rounded fp32 evaluation: {int(d_hi.max())}"
+    rel = (g.float() - h).abs() / h.abs().clamp_min(1e-30)
+    assert rel.max() <= 2.0 ** -8 + 1e-3  # half an ulp of the final rounding + 1e-3 of fp32 math
+    d_ref = ulp16_diff(g, r)
+    assert d_ref.max() <= 8 and (d_ref > 2).float().mean() < 2e-2, (int(d_ref.max()), float((d_ref > 2).float().mean()))
+    # the forced positions carry the reference's sentinel: round(max + 1)
+    sentinel = (g.float().max() + 1).to(dtype)
+    assert (got[..., forced] == sentinel).all()
+
+
+def _jaccard(a: torch.Tensor, b: torch.Tensor, S: int) -> float:
+    ma = torch.zeros(a.shape[:-1] + (S,), dtype=torch.bool).scatter_(-1, a.long(), True)
+    mb = torch.zeros(b.shape[:-1] + (S,), dtype=torch.bool).scatter_(-1, b.long(), True)
+    return float((ma & mb).sum()) / float((ma | mb).sum())
+
+
+# ---------------------------------------------------------------------------------------------------
+# ExpectedAttention
+# ---------------------------------------------------------------------------------------------------
+def test_expected_attention_scores_vs_golden(golden):
+    nat = _native()
+    k, v = golden.t("keys").to(DEV), golden.t("values").to(DEV)
+    mu, cov = golden.t("ea_mu"), golden.t("ea_cov")
+    variants = [
+        ("ea_scores", cov, 0.0, True),
+        ("ea_scores_nocov_novnorm", None, 0.0, False),
+        ("ea_scores_eps", cov, 1e-2, True),
+    ]
+    for name, c, eps, vn in variants:
+        got = nat.expected_attention_score(k, v, mu.to(DEV), None if c is None else c.to(DEV), eps, 4, vn).cpu()
+        hi = O.expected_attention_scores_fp32(golden.t("keys"), golden.t("values"), mu, c, eps, 4, vn)
+        _assert_scores_close(got, golden.t(name), hi, slice(0, 4), golden.dtype)
+
+
+def test_expected_attention_compress_vs_golden(golden):
+    nat = _native()
+    k, v = golden.t("keys").to(DEV), golden.t("values").to(DEV)
+    mu, cov = golden.t("ea_mu").to(DEV), golden.t("ea_cov").to(DEV)
+    ref_scores = golden.t("ea_scores")
+    for i, r in enumerate(golden.ratios):
+        n_kept = O.kept_count(golden.S, r)
+        k_out, v_out, idx, scores = nat.expected_attention_compress(
+            k, v, mu, cov, 0.0, 4, True, n_kept, return_indices=True, return_scores=True)
+        _check_compaction(k, v, k_out, v_out, idx)
+        idx_c = idx.cpu()
+        assert torch.equal(idx_c.long(), O.select_lowest_index_ties(scores.cpu(), n_kept))
+        assert (idx_c[..., :min(4, n_kept)] == torch.arange(min(4, n_kept))).all()  # sinks are kept
+        res = O.check_selection(ref_scores, idx_c, n_kept, ulp_slack=8)
+        assert res["ok"], res
+        assert _jaccard(idx_c, golden.t(f"ea_kept_{i}"), golden.S) > 0.93  # the reference's own 16-bit noise moves a few ranks
+
+
+def test_expected_attention_llama8b_shape_vs_fp32_oracle():
+    """Llama-3.1-8B layer shape (Hq=32, Hkv=8, D=128) at a length the fp32 oracle finishes in seconds."""
+    nat = _native()
+    torch.manual_seed(21)
+    B, H, Hq, S, D = 1, 8, 32, 6000, 128
+    k = torch.randn(B, H, S, D, dtype=torch.bfloat16)
+    v = torch.randn(B, H, S, D, dtype=torch.bfloat16)
+    mu = (0.5 * torch.randn(B, Hq, D)).to(torch.bfloat16)
+    a = torch.randn(B, Hq, D, D) / D ** 0.5
+    cov = (a @ a.transpose(-1, -2)).to(torch.bfloat16)
+    n_kept = O.kept_count(S, 0.7)
+    k_out, v_out, idx, scores = nat.expected_attention_compress(
+        k.to(DEV), v.to(DEV), mu.to(DEV), cov.to(DEV), 0.0, 4, True, n_kept, return_indices=True, return_scores=True)
+    _check_compaction(k, v, k_out, v_out, idx)
+    hi = O.expected_attention_scores_fp32(k, v, mu, cov, 0.0, 4, True)
+    ref = O.expected_attention_scores(k, v, mu, cov, 0.0, 4, True)
+    _assert_scores_close(scores.cpu(), ref, hi, slice(0, 4), torch.bfloat16)
+    assert torch.equal(idx.cpu().long(), O.select_lowest_index_ties(scores.cpu(), n_kept))
