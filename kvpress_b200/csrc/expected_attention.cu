@@ -23,8 +23,17 @@
 
 namespace kvp {
 
+#ifdef KVP_EA_PROFILE
+__device__ long long g_ea_prof[32];
+#define EA_T0() const long long _t0 = clock64()
+#define EA_ACC(slot) do { if (blockIdx.x == 0) g_ea_prof[slot] += clock64() - _t0; } while (0)
+#else
+#define EA_T0() do {} while (0)
+#define EA_ACC(slot) do {} while (0)
+#endif
+
 constexpr int kEaTile = 128;      // key rows per MMA tile (M)
-constexpr int kEaThreads = 384;   // 12 warps: TMA, MMA, TMEM-alloc, spare, 4 epilogue, 4 V-norm
+constexpr int kEaThreads = 512;   // 16 warps: TMA, MMA, TMEM-alloc, spare, 2x4 epilogue, 4 V-norm
 constexpr int kEaMaxParts = 160;  // upper bound on CTAs per (b,h) row (>= SM count)
 
 struct EaScratch {
@@ -67,9 +76,13 @@ struct EaSmem {
     static constexpr int kStages = 2;
     static constexpr int kCovOff = 0;
     static constexpr int kStageOff = kCovBytes;
-    static constexpr int kBiasOff = kStageOff + kStages * kStageBytes;  // float [G][D]
-    static constexpr int kBarOff = kBiasOff + G * D * 4;
-    static constexpr int kTotal = kBarOff + 256;
+    // extra K=16 step that adds 2 sqrt(d) mu_g[n] to Y_g[.,n] inside the MMA: A-extra = [128 x 16]
+    // with columns 0,1 = 1.0; B-extra = [G*D x 16] with column 0/1 = hi/lo halves of the bias
+    static constexpr int kAxOff = kStageOff + kStages * kStageBytes;  // 128 rows * 32 B
+    static constexpr int kBxOff = kAxOff + kEaTile * 32;                // G*D rows * 32 B
+    static constexpr int kBarOff = kBxOff + G * D * 32;
+    static constexpr int kTotal = kBarOff + 512;
+    static_assert(kTotal + 1024 <= 227 * 1024, "shared memory budget");
 };
 
 template <typename T, int D, int G>
@@ -85,7 +98,8 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* s_cov = smem + L::kCovOff;
     unsigned char* s_stage = smem + L::kStageOff;
-    float* s_bias = reinterpret_cast<float*>(smem + L::kBiasOff);
+    unsigned char* s_ax = smem + L::kAxOff;
+    unsigned char* s_bx = smem + L::kBxOff;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
     uint64_t* k_full = bars;         // [2]
     uint64_t* k_empty = bars + 2;    // [2]
@@ -93,18 +107,18 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     uint64_t* t_empty = bars + 6;    // [2]
     uint64_t* cov_full = bars + 8;   // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-    float* s_red = reinterpret_cast<float*>(bars + 12);  // [4 warps][G][2]
+    float* s_red = reinterpret_cast<float*>(bars + 12);  // [8 warps][2 heads][2], then [2 wg][2][2]
 
     constexpr int kHalves = (G + 1) / 2;          // head pairs per tile
-    constexpr int kHeadsPerHalf = (G >= 2) ? 2 : 1;
-    constexpr int kN = kHeadsPerHalf * D;         // MMA N
+    constexpr int HPH = (G >= 2) ? 2 : 1;         // heads per half
+    constexpr int kN = HPH * D;                   // MMA N
     constexpr int kBufCols = 256;
+    constexpr int kChunks = D / 32;
     static_assert(kN <= 256, "two heads must fit one MMA");
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // ---- which (row, tile range) this CTA owns ----------------------------------------------------
-    // rows are visited round-robin when there are more rows than CTA groups
+    // ---- which (row, tile range) this CTA owns; rows are visited round-robin -----------------------
     const int n_groups = gridDim.x / ctas_per_row;  // concurrent rows
     const int group = blockIdx.x / ctas_per_row;
     const int part = blockIdx.x % ctas_per_row;
@@ -114,9 +128,9 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         umma::prefetch_tmap(&mapCov);
         for (int i = 0; i < 2; ++i) {
             umma::mbar_init(&k_full[i], 1);
-            umma::mbar_init(&k_empty[i], 1 + 4);  // MMA commit + 4 epilogue warps
+            umma::mbar_init(&k_empty[i], 1 + 8);  // MMA commit + 8 epilogue warps
             umma::mbar_init(&t_full[i], 1);
-            umma::mbar_init(&t_empty[i], 4);
+            umma::mbar_init(&t_empty[i], 4);      // the 4 warps of the warpgroup that drained it
         }
         umma::mbar_init(cov_full, 1);
         umma::mbar_fence_init();
@@ -134,18 +148,30 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     const float bias_scale = 2.0f * sqrtf((float)D);
 
     // pipeline state carried across rows (barriers keep flipping)
-    uint32_t k_it = 0;  // tiles processed by this role
-    uint32_t h_it = 0;  // halves processed by this role
+    uint32_t k_it = 0;  // tiles seen by this role
+    uint32_t h_it = 0;  // halves seen by this role
     uint32_t cov_it = 0;
 
     for (int row = group; row < R; row += n_groups) {
         const int b = row / H, h = row % H;
         const int hq0 = b * Hq + h * G;  // first query head of this kv head in [B*Hq]
-        // everyone: previous row's epilogue has finished reading s_bias / s_cov
-        __syncthreads();
-        for (int i = tid; i < G * D; i += kEaThreads)
-            s_bias[i] = bias_scale * F16Traits<T>::to_float(
-                                         reinterpret_cast<const uint16_t*>(mu)[(size_t)hq0 * D + i]);
+        __syncthreads();  // previous row fully drained (s_bias, s_cov, s_red reusable)
+        for (int n = tid; n < G * D; n += kEaThreads) {
+            const float bias = bias_scale * F16Traits<T>::to_float(
+                                                reinterpret_cast<const uint16_t*>(mu)[(size_t)hq0 * D + n]);
+            const uint16_t hi = F16Traits<T>::from_float(bias);
+            const uint16_t lo = F16Traits<T>::from_float(bias - F16Traits<T>::to_float(hi));
+            *reinterpret_cast<uint4*>(s_bx + umma::k16_noswizzle_offset(n, 0)) =
+                make_uint4((uint32_t)hi | ((uint32_t)lo << 16), 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(s_bx + umma::k16_noswizzle_offset(n, 1)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (tid < kEaTile) {
+            const uint32_t one = (uint32_t)F16Traits<T>::from_float(1.0f);
+            *reinterpret_cast<uint4*>(s_ax + umma::k16_noswizzle_offset(tid, 0)) =
+                make_uint4(one | (one << 16), 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(s_ax + umma::k16_noswizzle_offset(tid, 1)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> UMMA reads
         __syncthreads();
 
         if (warp == 0) {
@@ -158,7 +184,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                                           kp * 64, 0, hq0 + g);
                 for (int t = t_begin; t < t_end; ++t, ++k_it) {
                     const int stage = k_it & 1;
-                    umma::mbar_wait(&k_empty[stage], ((k_it >> 1) & 1) ^ 1);
+                    { EA_T0(); umma::mbar_wait(&k_empty[stage], ((k_it >> 1) & 1) ^ 1); EA_ACC(0); }
                     umma::mbar_arrive_expect_tx(&k_full[stage], L::kStageBytes);
                     for (int kp = 0; kp < L::kPanels; ++kp)
                         umma::tma_load_4d(s_stage + stage * L::kStageBytes + kp * (kEaTile * 128),
@@ -168,18 +194,17 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         } else if (warp == 1) {
             // ===== MMA issuer =====
             if (lane == 0) {
-                const uint32_t idesc =
-                    umma::instr_desc_f16(kEaTile, kN, F16Traits<T>::kMmaFormat);
+                const uint32_t idesc = umma::instr_desc_f16(kEaTile, kN, F16Traits<T>::kMmaFormat);
                 umma::mbar_wait(cov_full, cov_it & 1);
                 for (int t = t_begin; t < t_end; ++t, ++k_it) {
                     const int stage = k_it & 1;
-                    umma::mbar_wait(&k_full[stage], (k_it >> 1) & 1);
+                    { EA_T0(); umma::mbar_wait(&k_full[stage], (k_it >> 1) & 1); EA_ACC(1); }
                     umma::fence_after_sync();
                     const uint32_t a_base = umma::smem_u32(s_stage + stage * L::kStageBytes);
 #pragma unroll 1
                     for (int half = 0; half < kHalves; ++half, ++h_it) {
                         const int buf = h_it & 1;
-                        umma::mbar_wait(&t_empty[buf], ((h_it >> 1) & 1) ^ 1);
+                        { EA_T0(); umma::mbar_wait(&t_empty[buf], ((h_it >> 1) & 1) ^ 1); EA_ACC(2); }
                         umma::fence_after_sync();
 #pragma unroll
                         for (int k = 0; k < D / 16; ++k) {
@@ -187,102 +212,130 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                             const uint64_t da =
                                 umma::smem_desc_sw128(a_base + kp * (kEaTile * 128) + kk * 32);
                             const uint64_t db = umma::smem_desc_sw128(
-                                umma::smem_u32(s_cov + (kp * G + half * kHeadsPerHalf) * L::kCovHeadPanel) +
-                                kk * 32);
+                                umma::smem_u32(s_cov + (kp * G + half * HPH) * L::kCovHeadPanel) + kk * 32);
                             umma::mma_f16_ss(tmem + buf * kBufCols, da, db, idesc, k > 0);
                         }
+                        umma::mma_f16_ss(tmem + buf * kBufCols,
+                                         umma::smem_desc_k16_noswizzle(umma::smem_u32(s_ax)),
+                                         umma::smem_desc_k16_noswizzle(
+                                             umma::smem_u32(s_bx) + (half * HPH * D / 8) * 256),
+                                         idesc, 1);
                         umma::mma_commit(&t_full[buf]);
                     }
                     umma::mma_commit(&k_empty[stage]);
                 }
             }
             ++cov_it;
-        } else if (warp >= 4 && warp < 8) {
-            // ===== epilogue: thread = key row of the tile =====
-            const int ew = warp - 4;
+        } else if (warp >= 4 && warp < 12) {
+            // ===== epilogue: two warpgroups, warpgroup wg drains TMEM buffer wg; thread = key row =====
+            const int wg = (warp - 4) >> 2;
+            const int ew = warp & 3;       // TMEM lane quarter this warp may access
             const int r = ew * 32 + lane;  // row in tile == TMEM lane
             const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
-            float run_m[G], run_z[G];
+            float run_m[HPH], run_z[HPH];
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                run_m[g] = -INFINITY;
-                run_z[g] = 0.f;
+            for (int q = 0; q < HPH; ++q) {
+                run_m[q] = -INFINITY;
+                run_z[q] = 0.f;
             }
             for (int t = t_begin; t < t_end; ++t, ++k_it) {
                 const int stage = k_it & 1;
-                umma::mbar_wait(&k_full[stage], (k_it >> 1) & 1);
                 const unsigned char* krow = s_stage + stage * L::kStageBytes;
                 const int s = t * kEaTile + r;
                 const bool valid = (s >= n_sink) && (s < S);
+                bool waited_k = false;
 #pragma unroll 1
                 for (int half = 0; half < kHalves; ++half, ++h_it) {
                     const int buf = h_it & 1;
-                    umma::mbar_wait(&t_full[buf], (h_it >> 1) & 1);
+                    if (buf != wg) continue;
+                    if (!waited_k) {
+                        EA_T0();
+                        umma::mbar_wait(&k_full[stage], (k_it >> 1) & 1);
+                        if (warp == 4 && lane == 0) EA_ACC(3);
+                        waited_k = true;
+                    }
+                    {
+                        EA_T0();
+                        umma::mbar_wait(&t_full[buf], (h_it >> 1) & 1);
+                        if (warp == 4 && lane == 0) EA_ACC(4);
+                    }
+                    EA_T0();
                     umma::fence_after_sync();
-                    float acc[kHeadsPerHalf];
+                    const uint32_t tbase = tmem + lane_base + buf * kBufCols;
+                    uint64_t acc2[HPH][4];  // 4 independent fp32x2 accumulators per head
 #pragma unroll
-                    for (int q = 0; q < kHeadsPerHalf; ++q) acc[q] = 0.f;
-#pragma unroll 1
-                    for (int c0 = 0; c0 < D; c0 += 32) {
-                        uint32_t y[kHeadsPerHalf][32];
+                    for (int q = 0; q < HPH; ++q)
 #pragma unroll
-                        for (int q = 0; q < kHeadsPerHalf; ++q)
-                            umma::tmem_ld32(tmem + lane_base + buf * kBufCols + q * D + c0, y[q]);
-                        // the k row chunk while the TMEM loads are in flight
-                        float kf[32];
-                        const int kp = c0 >> 6;
+                        for (int j = 0; j < 4; ++j) acc2[q][j] = 0ull;
+                    // software pipeline over steps (16-column chunk c, head q): the TMEM load of step i+1
+                    // is in flight while step i is being reduced
+                    constexpr int kC16 = D / 16;
+                    uint32_t y[2][16];
+                    umma::tmem_ld16(tbase, y[0]);
 #pragma unroll
-                        for (int ch = 0; ch < 4; ++ch) {
-                            const uint4 v = *reinterpret_cast<const uint4*>(
-                                krow + kp * (kEaTile * 128) +
-                                umma::sw128_offset(r, ((c0 & 63) >> 3) + ch));
-                            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                    for (int c = 0; c < kC16; ++c) {
+                        // k values of this row for columns [16c, 16c+16) as 8 fp32 pairs
+                        uint64_t k2[8];
+                        {
+                            const int c0 = c * 16;
+                            const int kpanel = c0 >> 6;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 f = F16Traits<T>::unpack2(w4[j]);
-                                kf[ch * 8 + j * 2] = f.x;
-                                kf[ch * 8 + j * 2 + 1] = f.y;
+                            for (int ch = 0; ch < 2; ++ch) {
+                                const uint4 v = *reinterpret_cast<const uint4*>(
+                                    krow + kpanel * (kEaTile * 128) +
+                                    umma::sw128_offset(r, ((c0 & 63) >> 3) + ch));
+                                k2[ch * 4] = pack_f32x2(F16Traits<T>::unpack2(v.x));
+                                k2[ch * 4 + 1] = pack_f32x2(F16Traits<T>::unpack2(v.y));
+                                k2[ch * 4 + 2] = pack_f32x2(F16Traits<T>::unpack2(v.z));
+                                k2[ch * 4 + 3] = pack_f32x2(F16Traits<T>::unpack2(v.w));
                             }
                         }
-                        umma::tmem_ld_wait();
 #pragma unroll
-                        for (int q = 0; q < kHeadsPerHalf; ++q) {
-                            const float* bias = s_bias + (half * kHeadsPerHalf + q) * D + c0;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 bq = *reinterpret_cast<const float4*>(bias + j);
-                                acc[q] = fmaf(kf[j], __uint_as_float(y[q][j]) + bq.x, acc[q]);
-                                acc[q] = fmaf(kf[j + 1], __uint_as_float(y[q][j + 1]) + bq.y, acc[q]);
-                                acc[q] = fmaf(kf[j + 2], __uint_as_float(y[q][j + 2]) + bq.z, acc[q]);
-                                acc[q] = fmaf(kf[j + 3], __uint_as_float(y[q][j + 3]) + bq.w, acc[q]);
+                        for (int q = 0; q < HPH; ++q) {
+                            constexpr int kSteps = kC16 * HPH;
+                            const int step = c * HPH + q;
+                            umma::tmem_ld_wait();
+                            if (step + 1 < kSteps) {
+                                const int cn = (step + 1) / HPH, qn = (step + 1) % HPH;
+                                umma::tmem_ld16(tbase + qn * D + cn * 16, y[(step + 1) & 1]);
                             }
+                            const uint32_t* yy = y[step & 1];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                acc2[q][j & 3] = fma_f32x2(k2[j], pack_u32x2(yy[2 * j], yy[2 * j + 1]), acc2[q][j & 3]);
                         }
                     }
+                    float acc[HPH];
+#pragma unroll
+                    for (int q = 0; q < HPH; ++q) {
+                        const float2 a0 = unpack_f32x2(acc2[q][0]), a1 = unpack_f32x2(acc2[q][1]);
+                        const float2 a2 = unpack_f32x2(acc2[q][2]), a3 = unpack_f32x2(acc2[q][3]);
+                        acc[q] = ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+                    }
+                    if (warp == 4 && lane == 0) EA_ACC(5);
                     // accumulator buffer can be overwritten by the next MMA
                     umma::fence_before_sync();
                     __syncwarp();
                     if (lane == 0) umma::mbar_arrive(&t_empty[buf]);
 #pragma unroll
-                    for (int q = 0; q < kHeadsPerHalf; ++q) {
-                        const int g = half * kHeadsPerHalf + q;
-                        if (g < G) {
-                            const float lg = acc[q] * inv_2d;
-                            if (valid) {
-                                sc.logits[((size_t)row * G + g) * S_pad + s] = lg;
-                                const float m_new = fmaxf(run_m[g], lg);
-                                run_z[g] = run_z[g] * __expf(run_m[g] - m_new) + __expf(lg - m_new);
-                                run_m[g] = m_new;
-                            }
+                    for (int q = 0; q < HPH; ++q) {
+                        const int g = half * HPH + q;
+                        const float lg = acc[q] * inv_2d;
+                        if (valid && g < G) {
+                            sc.logits[((size_t)row * G + g) * S_pad + s] = lg;
+                            const float m_new = fmaxf(run_m[q], lg);
+                            run_z[q] = run_z[q] * __expf(run_m[q] - m_new) + __expf(lg - m_new);
+                            run_m[q] = m_new;
                         }
                     }
                 }
                 __syncwarp();
-                if (lane == 0) umma::mbar_arrive(&k_empty[stage]);
+                if (lane == 0) umma::mbar_arrive(&k_empty[stage]);  // done with (or skipped) this K tile
             }
-            // ---- CTA-level (max, sum-exp) per head -> partial[row][g][part] --------------------------
+            // ---- warp-level (max, sum-exp) per head slot -> shared ---------------------------------------
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                float m = run_m[g], z = run_z[g];
+            for (int q = 0; q < HPH; ++q) {
+                float m = run_m[q], z = run_z[q];
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) {
                     const float m2 = __shfl_xor_sync(0xFFFFFFFFu, m, off);
@@ -292,60 +345,97 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     m = mn;
                 }
                 if (lane == 0) {
-                    s_red[(ew * G + g) * 2] = m;
-                    s_red[(ew * G + g) * 2 + 1] = z;
+                    s_red[((warp - 4) * 2 + q) * 2] = m;
+                    s_red[((warp - 4) * 2 + q) * 2 + 1] = z;
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-            if (ew == 0 && lane < G) {
-                float m = -INFINITY, z = 0.f;
-                for (int w = 0; w < 4; ++w) {
-                    const float m2 = s_red[(w * G + lane) * 2], z2 = s_red[(w * G + lane) * 2 + 1];
-                    const float mn = fmaxf(m, m2);
-                    z = (mn == -INFINITY) ? 0.f : z * __expf(m - mn) + z2 * __expf(m2 - mn);
-                    m = mn;
-                }
-                sc.partial[((size_t)row * G + lane) * n_parts + part] = make_float2(m, z);
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-        } else if (warp >= 8) {
-            // ===== V norms for the same tiles (plain streaming loads, 16 in flight per lane) =====
+        } else if (warp >= 12) {
+            // ===== V norms for the same tiles: software-pipelined streaming loads. Each warp-wide load
+            // covers 2 rows (16 lanes x 16 B per row); a "group" is 8 such loads (16 rows per warp,
+            // 64 rows per 4 warps); the loads of group i+1 are in flight while group i is reduced, and
+            // the 4-level shuffle reductions of the 8 rows of a group run in lockstep (ILP 8). =====
             if (use_vnorm) {
-                const int vw = warp - 8;
+                EA_T0();
+                const int vw = warp - 12;
                 const int sub = lane & 15, rsel = lane >> 4;
                 constexpr int nvec = D / 8;
+                constexpr int GRP = 6;                               // loads per lane per group
+                constexpr int ROWS_PER_GRP = GRP * 2 * 4;            // 64 rows per group (4 warps)
                 const T* vbase = V + (int64_t)b * vs.b + (int64_t)h * vs.h + sub * 8;
                 const uint64_t pol = l2_policy_evict_first();
-                for (int t = t_begin; t < t_end; ++t) {
-                    // 128 rows per tile, 4 warps x 2 rows per load => 16 loads per lane
-                    int4 v[16];
+                const int s_lo = t_begin * kEaTile;
+                const int s_hi = min(S, t_end * kEaTile);
+                const int n_grp = (s_hi - s_lo + ROWS_PER_GRP - 1) / ROWS_PER_GRP;
+                // ring of three register buffers: one being reduced, two in flight
+                int4 buf[3][GRP];
+                auto issue = [&](int4 (&dst)[GRP], int grp) {
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        const int s = t * kEaTile + u * 8 + vw * 2 + rsel;
-                        v[u] = make_int4(0, 0, 0, 0);
-                        if (s < S && sub < nvec) v[u] = ldg_hint(vbase + (int64_t)s * vs.s, pol);
+                    for (int u = 0; u < GRP; ++u) {
+                        const int s = s_lo + grp * ROWS_PER_GRP + u * 8 + vw * 2 + rsel;
+                        dst[u] = make_int4(0, 0, 0, 0);
+                        if (s < s_hi && sub < nvec) dst[u] = ldg_hint(vbase + (int64_t)s * vs.s, pol);
                     }
+                };
+                auto reduce = [&](const int4 (&src)[GRP], int grp) {
+                    float ss[GRP];
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        const uint32_t w4[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z,
-                                                (uint32_t)v[u].w};
-                        float ss = 0.f;
+                    for (int u = 0; u < GRP; ++u) {
+                        const uint32_t w4[4] = {(uint32_t)src[u].x, (uint32_t)src[u].y, (uint32_t)src[u].z,
+                                                (uint32_t)src[u].w};
+                        uint64_t a2 = 0ull;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float2 f = F16Traits<T>::unpack2(w4[j]);
-                            ss = fmaf(f.x, f.x, ss);
-                            ss = fmaf(f.y, f.y, ss);
+                            const uint64_t f2 = pack_f32x2(F16Traits<T>::unpack2(w4[j]));
+                            a2 = fma_f32x2(f2, f2, a2);
                         }
+                        const float2 a = unpack_f32x2(a2);
+                        ss[u] = a.x + a.y;
+                    }
 #pragma unroll
-                        for (int off = 8; off >= 1; off >>= 1)
-                            ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
-                        const int s = t * kEaTile + u * 8 + vw * 2 + rsel;
-                        if (sub == 0 && s < S) sc.vnorm[(size_t)row * S_pad + s] = sqrtf(ss);
+                    for (int off = 8; off >= 1; off >>= 1) {
+#pragma unroll
+                        for (int u = 0; u < GRP; ++u) ss[u] += __shfl_xor_sync(0xFFFFFFFFu, ss[u], off);
+                    }
+#pragma unroll
+                    for (int u = 0; u < GRP; ++u) {
+                        const int s = s_lo + grp * ROWS_PER_GRP + u * 8 + vw * 2 + rsel;
+                        if (sub == 0 && s < s_hi) sc.vnorm[(size_t)row * S_pad + s] = sqrtf(ss[u]);
+                    }
+                };
+                if (n_grp > 0) issue(buf[0], 0);
+                if (n_grp > 1) issue(buf[1], 1);
+                // unrolled by 3 so the ring indices are compile-time constants (registers, not local memory)
+                for (int grp = 0; grp < n_grp; grp += 3) {
+                    if (grp + 2 < n_grp) issue(buf[2], grp + 2);
+                    reduce(buf[0], grp);
+                    if (grp + 1 < n_grp) {
+                        if (grp + 3 < n_grp) issue(buf[0], grp + 3);
+                        reduce(buf[1], grp + 1);
+                    }
+                    if (grp + 2 < n_grp) {
+                        if (grp + 4 < n_grp) issue(buf[1], grp + 4);
+                        reduce(buf[2], grp + 2);
                     }
                 }
+                if (warp == 12 && lane == 0) EA_ACC(6);
             }
         }
-        if (warp == 0) ++cov_it;  // keep the producer's notion of the cov phase in step (unused there)
+        // ---- CTA-level softmax statistics of this (row, part) -> partial[row][g][part] ---------------
+        __syncthreads();
+        if (tid < G) {
+            // head g was accumulated in slot q of the warps of: both warpgroups (one half per tile,
+            // tiles alternate) or warpgroup g / HPH (two halves per tile)
+            const int g = tid, q = g % HPH;
+            float m = -INFINITY, z = 0.f;
+            for (int w = 0; w < 8; ++w) {
+                if (kHalves == 2 && (w >> 2) != g / HPH) continue;
+                const float m2 = s_red[(w * 2 + q) * 2], z2 = s_red[(w * 2 + q) * 2 + 1];
+                const float mn = fmaxf(m, m2);
+                z = (mn == -INFINITY) ? 0.f : z * __expf(m - mn) + z2 * __expf(m2 - mn);
+                m = mn;
+            }
+            sc.partial[((size_t)row * G + g) * n_parts + part] = make_float2(m, z);
+        }
     }
 
     umma::fence_before_sync();
@@ -626,6 +716,17 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
     if (scores_out != nullptr) e = launch_fill_sentinel(dtype, scores_out, d.R, d.S, 0, n_sink, ws, st);
     return e;
 }
+
+#ifdef KVP_EA_PROFILE
+extern "C" void kvp_debug_ea_profile(long long* out, int reset) {
+    if (reset) {
+        long long z[32] = {0};
+        cudaMemcpyToSymbol(g_ea_prof, z, sizeof(z));
+    } else {
+        cudaMemcpyFromSymbol(out, g_ea_prof, 32 * sizeof(long long));
+    }
+}
+#endif
 
 cudaError_t launch_ea_score(const Dims& d, int dtype, const void* K, const void* V, const void* mu,
                             const void* cov, float eps, int n_sink, int use_vnorm,

@@ -98,6 +98,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -115,6 +125,21 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;             // SWIZZLE_128B
     return d;
+}
+// Descriptor of a K-major operand that is only 16 elements (32 B) wide, stored WITHOUT swizzle in the
+// canonical "interleaved" form: core matrix = 8 rows x 16 B (rows 16 B apart, 128 B total); the
+// second 16-byte K half of the same 8 rows sits LBO = 128 B further, the next 8-row group SBO = 256 B
+// further. Row r, half j lives at (r/8)*256 + j*128 + (r%8)*16.
+__device__ __forceinline__ uint64_t smem_desc_k16_noswizzle(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)(128 >> 4) << 16;    // LBO
+    d |= (uint64_t)(256 >> 4) << 32;    // SBO
+    d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+    return d;                           // layout type 0 = SWIZZLE_NONE
+}
+__device__ __forceinline__ uint32_t k16_noswizzle_offset(int row, int half) {
+    return (uint32_t)((row >> 3) * 256 + half * 128 + (row & 7) * 16);
 }
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): fp32 accumulate, A and B
 // K-major, `ab_format` 0 = fp16, 1 = bf16.
@@ -140,6 +165,29 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+}  // namespace umma
+
+// ---- packed fp32x2 arithmetic (sm_100: one FFMA2 issues two fp32 FMAs) -----------------------------
+__device__ __forceinline__ uint64_t pack_u32x2(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float2 v) {
+    return pack_u32x2(__float_as_uint(v.x), __float_as_uint(v.y));
+}
+__device__ __forceinline__ float2 unpack_f32x2(uint64_t v) {
+    uint32_t lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+    return make_float2(__uint_as_float(lo), __uint_as_float(hi));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+namespace umma {
 // Byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a SWIZZLE_128B panel whose rows
 // are 128 B: what generic loads must use to read a TMA-written panel.
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {

@@ -1,0 +1,24 @@
+"""Role-level wait/compute cycle counters of ea_logits_kernel (block 0), built with -DKVP_EA_PROFILE."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["KVPRESS_B200_LIB"] = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin", "libkvp_prof.so")
+import torch
+from kvpress_b200 import native
+import bench
+lib = native.load()
+w = bench.WORKLOADS["ea_128k"]
+K, V, extra = bench.make_inputs(w, "cuda:0", 1)
+n_kept = bench.kept_count(w["S"], w["ratio"])
+for _ in range(3):
+    bench.run_native(w, K, V, extra, n_kept)
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * 32)()
+lib.kvp_debug_ea_profile(buf, 1)
+bench.run_native(w, K, V, extra, n_kept)
+torch.cuda.synchronize()
+lib.kvp_debug_ea_profile(buf, 0)
+names = ["producer wait k_empty", "mma wait k_full", "mma wait t_empty", "epi(WG0 w4) wait k_full", "epi wait t_full",
+         "epi compute (per half)", "vnorm warp total"]
+tiles = 57
+for i, n in enumerate(names):
+    print(f"{n:28s} {buf[i]:10d} cycles  = {buf[i] / tiles:9.0f} per tile")
