@@ -1,0 +1,283 @@
+"""Host-side logic on CPU (no GPU): hook lifecycle, n_kept arithmetic, pipeline plumbing, DecodingPress
+scheduling — the reference's own tests (tests/test_press_call.py, tests/presses/test_presses.py:143-162,
+tests/test_pipeline.py, tests/test_decoding_compression.py) re-hosted on random-init models.
+The CUDA library is replaced by the oracle-backed stand-in of tests/cpu_backend.py (monkeypatch)."""
+import logging
+
+import pytest
+import torch
+from transformers import DynamicCache
+
+import kvpress_b200
+from kvpress_b200 import (DecodingPress, ExpectedAttentionPress, KnormPress, KVPressTextGenerationPipeline,
+                          ScorerPress, SnapKVPress, StreamingLLMPress, native)
+from kvpress_b200.presses.decoding_press import find_target_compression_ratio
+from kvpress_b200.presses.scorer_press import kept_count
+from oracle import press_oracle as O
+from tests import cpu_backend
+from tests.tiny_models import tiny_llama, tiny_qwen3, word_tokenizer, words
+
+
+@pytest.fixture
+def backend(monkeypatch):
+    cpu_backend.install(monkeypatch)
+
+
+@pytest.fixture(scope="module")
+def model():
+    return tiny_llama()
+
+
+@pytest.fixture(scope="module")
+def pipe():
+    return KVPressTextGenerationPipeline(model=tiny_llama(), tokenizer=word_tokenizer())
+
+
+def test_product_refuses_cpu_tensors_without_backend():
+    k = torch.randn(1, 2, 64, 16)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        native.knorm_compress(k, k, 32)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        KnormPress(0.5).compress(None, None, k, k, None, {})
+
+
+def test_context_manager_adds_and_removes_hooks(model):
+    press = KnormPress(compression_ratio=0.2)
+    with press(model):
+        for layer in model.model.layers:
+            assert len(layer.self_attn._forward_hooks) == 1
+    for layer in model.model.layers:
+        assert len(layer.self_attn._forward_hooks) == 0
+
+
+def test_hooks_removed_when_forward_raises(model):
+    press = KnormPress(compression_ratio=0.2)  # no backend installed: compress raises on CPU
+    with pytest.raises(RuntimeError):
+        with press(model):
+            model(torch.randint(0, 200, (1, 32)), past_key_values=DynamicCache())
+    for layer in model.model.layers:
+        assert len(layer.self_attn._forward_hooks) == 0
+
+
+@pytest.mark.parametrize("press_cls", [KnormPress, StreamingLLMPress, SnapKVPress, ExpectedAttentionPress])
+@pytest.mark.parametrize("ratio", [0.0, 0.2, 0.5, 0.7])
+def test_compression_applies_only_inside_context(backend, model, press_cls, ratio):
+    press = press_cls(compression_ratio=ratio)
+    ids = torch.randint(0, 200, (2, 130))
+    with press(model):
+        cache = model(ids, past_key_values=DynamicCache()).past_key_values
+    want = kept_count(130, ratio)
+    for layer in cache.layers:
+        assert layer.keys.shape[2] == want == cache.get_seq_length()
+        assert layer.values.shape[2] == want
+    cache = model(ids, past_key_values=DynamicCache()).past_key_values
+    for layer in cache.layers:
+        assert layer.keys.shape[2] == 130
+
+
+def test_no_compression_while_decoding(backend, model):
+    press = KnormPress(compression_ratio=0.5)
+    ids = torch.randint(0, 200, (1, 64))
+    with press(model):
+        cache = model(ids, past_key_values=DynamicCache()).past_key_values
+        assert cache.get_seq_length() == 32
+        model(torch.randint(0, 200, (1, 1)), past_key_values=cache)  # decoding step: untouched
+        assert cache.get_seq_length() == 33
+        model(torch.randint(0, 200, (1, 7)), past_key_values=cache)  # multi-token continuation
+        assert cache.get_seq_length() == 40
+
+
+class StoreKnormPress(KnormPress):
+    """Overrides score(): compress() must then go through score() + the generic select path."""
+
+    def __post_init__(self):
+        super().__post_init__()
+        self.scores = []
+
+    def score(self, module, hidden_states, keys, values, attentions, kwargs):
+        s = -keys.norm(dim=-1)
+        self.scores.append(s)
+        return s
+
+
+def test_kept_keys_are_the_highest_scoring(backend, model):
+    """Reference tests/presses/test_presses.py:143-162."""
+    for ratio in [0.0, 0.2, 0.4, 0.6, 0.8]:
+        press = StoreKnormPress(compression_ratio=ratio)
+        with press(model):
+            cache = model(torch.randint(0, 200, (5, 256)), past_key_values=DynamicCache()).past_key_values
+        if ratio == 0:
+            assert press.scores == []  # early-out before scoring (scorer_press.py:86-87)
+            continue
+        assert len(press.scores) == len(cache.layers)
+        for scores, layer in zip(press.scores, cache.layers):
+            kept = -layer.keys.norm(dim=-1)
+            n = kept.shape[-1]
+            assert torch.allclose(scores.sort(-1).values[..., -n:], kept.sort(-1).values)
+
+
+def test_score_is_a_public_standalone_method(backend, model):
+    attn = model.model.layers[0].self_attn
+    attn.rotary_emb = model.model.rotary_emb
+    hidden = torch.randn(1, 100, model.config.hidden_size)
+    k = torch.randn(1, 2, 100, 16)
+    v = torch.randn(1, 2, 100, 16)
+    pe = model.model.rotary_emb(hidden, torch.arange(100)[None])
+    for press in (KnormPress(0.5), StreamingLLMPress(0.5), SnapKVPress(0.5, window_size=16),
+                  ExpectedAttentionPress(0.5)):
+        s = press.score(attn, hidden, k, v, None, {"position_embeddings": pe})
+        assert s.shape == (1, 2, 100)
+    press = KnormPress(0.3)
+    press.compression_ratio = 0.6  # wrappers mutate it in place
+    k2, v2 = press.compress(attn, hidden, k, v, None, {})
+    assert k2.shape[2] == kept_count(100, 0.6)
+
+
+def test_qwen3_prologue_uses_q_norm(backend):
+    qwen = tiny_qwen3()
+    ids = torch.randint(0, 200, (1, 150))
+    for press in (SnapKVPress(0.5, window_size=16), ExpectedAttentionPress(0.5)):
+        with press(qwen):
+            cache = qwen(ids, past_key_values=DynamicCache()).past_key_values
+        assert cache.get_seq_length() == 75
+    attn = qwen.model.layers[0].self_attn
+    hidden = torch.randn(1, 9, qwen.config.hidden_size)
+    from kvpress_b200.utils import get_prerope_query_states
+    got = get_prerope_query_states(attn, hidden)
+    want = O.prerope_queries(hidden, attn.q_proj.weight, 4, 16, q_norm_weight=attn.q_norm.weight,
+                             eps=attn.q_norm.variance_epsilon)
+    assert torch.allclose(got, want, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------
+# pipeline
+# ---------------------------------------------------------------------------------------------------
+def test_pipeline_lengths_and_logs(backend, pipe, caplog):
+    context = words(23, seed=1)
+    with caplog.at_level(logging.DEBUG):
+        out = pipe(context, question=words(3, seed=2), press=ExpectedAttentionPress(compression_ratio=0.4),
+                   max_new_tokens=5)
+    assert isinstance(out["answer"], str)
+    messages = [r.message for r in caplog.records]
+    n_ctx = 24  # bos + 23 words
+    assert f"Context Length: {n_ctx}" in messages
+    assert f"Compressed Context Length: {kept_count(n_ctx, 0.4)}" in messages
+
+
+def test_pipeline_questions_and_cache_invariance(backend, pipe):
+    context = words(200, seed=3)
+    cache = DynamicCache()
+    out = pipe(context, questions=[words(4, seed=4), words(5, seed=5)], press=KnormPress(0.5), cache=cache,
+               max_new_tokens=4)
+    assert len(out["answers"]) == 2
+    assert cache.get_seq_length() == kept_count(201, 0.5)  # answers were stripped from the cache again
+    keys_before = [layer.keys.clone() for layer in cache.layers]
+    pipe.generate_answer(torch.randint(0, 200, (1, 6)), cache, context_length=201, max_new_tokens=3)
+    pipe._remove_answer_from_cache(cache, [kept_count(201, 0.5)] * len(cache.layers))
+    for before, layer in zip(keys_before, cache.layers):
+        assert torch.equal(before, layer.keys)
+    with pytest.raises(AssertionError):
+        pipe(context, question="w3", questions=["w4"])
+
+
+def test_pipeline_matches_manual_prefill_and_greedy_decode(backend, pipe):
+    """Reference tests/test_generate.py: the pipeline answer equals a hand-rolled prefill + greedy loop."""
+    context, question = words(120, seed=6), words(4, seed=7)
+    press = KnormPress(0.5)
+    answer = pipe(context, question=question, press=press, max_new_tokens=6)["answer"]
+    tok, model = pipe.tokenizer, pipe.model
+    ctx_ids = tok.encode(tok.bos_token + context, return_tensors="pt", add_special_tokens=False)
+    q_ids = tok.encode(question + "\n", return_tensors="pt", add_special_tokens=False)
+    cache = DynamicCache()
+    with press(model):
+        model.model(input_ids=ctx_ids, past_key_values=cache)
+    pos = torch.arange(ctx_ids.shape[1], ctx_ids.shape[1] + q_ids.shape[1])[None]
+    out = model(input_ids=q_ids, past_key_values=cache, position_ids=pos)
+    ids = [out.logits[0, -1].argmax()]
+    for i in range(5):
+        out = model(input_ids=ids[-1].view(1, 1), past_key_values=cache, position_ids=pos[:, -1:] + 1 + i)
+        ids.append(out.logits[0, -1].argmax())
+        if ids[-1].item() == model.generation_config.eos_token_id:
+            break
+    assert answer == tok.decode(torch.stack(ids), skip_special_tokens=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# DecodingPress
+# ---------------------------------------------------------------------------------------------------
+def test_decoding_ratio_arithmetic():
+    """Reference tests/test_decoding_compression.py:236-271."""
+    assert kept_count(108, 0.5) == 54
+    r = find_target_compression_ratio(58, 54)
+    assert abs(r - (1 - 54 / 58)) < 1e-3 and kept_count(58, r) == 54
+    assert find_target_compression_ratio(40, 54) == 0.0
+    for q_len, target in [(2560, 2048), (4607, 2048), (131072, 39321), (2049, 2048), (3000, 1), (7, 3)]:
+        assert find_target_compression_ratio(q_len, target) == O.find_target_compression_ratio(q_len, target)
+
+
+@pytest.mark.parametrize("base", [KnormPress, StreamingLLMPress, SnapKVPress, ExpectedAttentionPress])
+def test_decoding_press_size_bounds(backend, pipe, base):
+    """target <= len <= target + interval - 1 after enough steps (reference :50-183)."""
+    kw = {"window_size": 4} if base is SnapKVPress else {}
+    press = DecodingPress(base_press=base(**kw), compression_interval=8, target_size=48)
+    cache = DynamicCache()
+    pipe(words(100, seed=8), question=words(3, seed=9), press=press, cache=cache, max_new_tokens=30)
+    # answers are stripped: inspect during generation instead
+    sizes = []
+    orig = press.forward_hook
+
+    def spy(module, inp, kwargs, output):
+        out = orig(module, inp, kwargs, output)
+        if module.layer_idx == 0:
+            sizes.append(kwargs["past_key_values"].get_seq_length(0))
+        return out
+
+    press.forward_hook = spy
+    pipe(words(100, seed=8), question=words(3, seed=9), press=press, cache=DynamicCache(), max_new_tokens=30)
+    assert min(sizes[8:]) >= 48 and max(sizes[8:]) <= 48 + 8 - 1
+    assert 48 in sizes
+    assert press.layer_step_counts == {} and press.hidden_states_buffer == {}  # reset() on exit
+
+
+def test_decoding_press_buffers_only_when_needed(backend, pipe):
+    cheap = DecodingPress(base_press=KnormPress(), compression_interval=4, target_size=32)
+    costly = DecodingPress(base_press=SnapKVPress(window_size=4), compression_interval=6, target_size=32)
+    seen = {}
+    for name, press in (("cheap", cheap), ("costly", costly)):
+        orig = press.forward_hook
+
+        def spy(module, inp, kwargs, output, press=press, orig=orig, name=name):
+            out = orig(module, inp, kwargs, output)
+            seen[name] = max(seen.get(name, 0), len(press.hidden_states_buffer[module.layer_idx]))
+            return out
+
+        press.forward_hook = spy
+        pipe(words(60, seed=10), question=words(2, seed=11), press=press, max_new_tokens=10)
+    assert seen["cheap"] == 0 and seen["costly"] > 0
+
+
+def test_decoding_press_rejects_multiple_questions(backend, pipe):
+    press = DecodingPress(base_press=KnormPress(), compression_interval=4, target_size=32)
+    with pytest.raises(ValueError):
+        pipe(words(50), questions=["w3", "w4"], press=press)
+    with pytest.raises(AssertionError):
+        DecodingPress(base_press=object())
+
+
+def test_public_surface():
+    for name in ["BasePress", "ScorerPress", "KnormPress", "SnapKVPress", "ExpectedAttentionPress",
+                 "StreamingLLMPress", "DecodingPress", "KVPressTextGenerationPipeline"]:
+        assert hasattr(kvpress_b200, name)
+    import dataclasses
+    defaults = {f.name: f.default for f in dataclasses.fields(SnapKVPress)}
+    assert defaults == {"compression_ratio": 0.0, "window_size": 64, "kernel_size": 5}
+    defaults = {f.name: f.default for f in dataclasses.fields(ExpectedAttentionPress)}
+    assert defaults == {"compression_ratio": 0.0, "n_future_positions": 512, "n_sink": 4, "use_covariance": True,
+                        "use_vnorm": True, "epsilon": 0.0}
+    assert {f.name: f.default for f in dataclasses.fields(StreamingLLMPress)} == {"compression_ratio": 0.0, "n_sink": 4}
+    d = {f.name: f.default for f in dataclasses.fields(DecodingPress) if f.name != "base_press"}
+    assert d == {"compression_interval": 512, "target_size": 2048, "hidden_states_buffer_size": 256}
+    from transformers.pipelines import PIPELINE_REGISTRY
+    assert "kv-press-text-generation" in PIPELINE_REGISTRY.get_supported_tasks()
+    with pytest.raises(AssertionError):
+        ScorerPress(compression_ratio=1.0)
