@@ -226,6 +226,27 @@ def cpu_leg(w: dict, budget_s: float, max_reps: int = 3):
 
 
 # --------------------------------------------------------------------------------------------------
+# multi-rank bookkeeping (no data-path collective: ranks own disjoint batch shards)
+# --------------------------------------------------------------------------------------------------
+def rank_seed(rank: int, i: int = 0) -> int:
+    """Every rank synthesises its own shard; seeds never collide across ranks / input sets."""
+    return 1234 + 1000 * rank + i
+
+
+def max_over_ranks(ms_local: float, dist, device) -> float:
+    """The step time of the job is the slowest rank's device time."""
+    t = torch.tensor([ms_local], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_tokens_per_s(tokens_per_rank_step: int, world: int, ms_per_step: float) -> float:
+    """Weak scaling: every rank processes tokens_per_rank_step per step; value is the job aggregate."""
+    return tokens_per_rank_step * world / (ms_per_step * 1e-3)
+
+
+# --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -286,7 +307,7 @@ def main():
     # enough distinct input sets that consecutive steps never find their K/V in L2
     bytes_per_set = 2 * w["B"] * w["Hkv"] * w["S"] * w["D"] * 2
     n_sets = max(1, min(8, -(-4 * L2_BYTES // bytes_per_set)))
-    sets = [make_inputs(w, device, 1234 + 1000 * rank + i) for i in range(n_sets)]
+    sets = [make_inputs(w, device, rank_seed(rank, i)) for i in range(n_sets)]
     flush_note = (f"{n_sets} rotating input sets x {bytes_per_set / 2**20:.0f} MiB (> L2) so no step re-reads "
                   "cached K/V" if n_sets > 1 else f"inputs {bytes_per_set / 2**20:.0f} MiB per step > 126 MiB L2")
     config["l2"] = flush_note
@@ -309,14 +330,10 @@ def main():
         stop.record()
         torch.cuda.synchronize()
     barrier()
-    ms_total = start.elapsed_time(stop)
-    t = torch.tensor([ms_total], device=device, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = max_over_ranks(start.elapsed_time(stop), dist, device)
     ms_per_step = ms_total / args.steps
     tokens_per_step = w["B"] * w["S"] * world
-    value = tokens_per_step / (ms_per_step * 1e-3)
+    value = whole_job_tokens_per_s(w["B"] * w["S"], world, ms_per_step)
 
     # roofline of one compress call on one GPU
     peaks = load_peaks()
@@ -355,10 +372,7 @@ def main():
         stop.record()
         torch.cuda.synchronize()
         barrier()
-        t = torch.tensor([start.elapsed_time(stop)], device=device, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item()) / e2e_steps
+        e2e_ms = max_over_ranks(start.elapsed_time(stop), dist, device) / e2e_steps
         e2e = {
             "value": tokens_per_step / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
             "h2d_bytes_per_step": 2 * Kh.numel() * 2, "d2h_bytes_per_step": 2 * out_k.numel() * 2,
