@@ -177,7 +177,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def __enter__(self):
         if self._nv is not None:
@@ -250,7 +250,7 @@ def whole_job_tokens_per_s(tokens_per_rank_step: int, world: int, ms_per_step: f
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default=os.environ.get("KVP_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=list(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

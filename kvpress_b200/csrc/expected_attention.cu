@@ -373,7 +373,11 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     for (int u = 0; u < GRP; ++u) {
                         const int s = s_lo + grp * ROWS_PER_GRP + u * 8 + vw * 2 + rsel;
                         dst[u] = make_int4(0, 0, 0, 0);
+#ifdef KVP_EA_VPLAIN
+                        if (s < s_hi && sub < nvec) dst[u] = ldg_plain(vbase + (int64_t)s * vs.s);
+#else
                         if (s < s_hi && sub < nvec) dst[u] = ldg_hint(vbase + (int64_t)s * vs.s, pol);
+#endif
                     }
                 };
                 auto reduce = [&](const int4 (&src)[GRP], int grp) {

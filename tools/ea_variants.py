@@ -1,6 +1,8 @@
 """Times kvp_expected_attention_score variants at the 128k workload (CUDA events, best of N)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if len(sys.argv) > 1:
+    os.environ["KVPRESS_B200_LIB"] = sys.argv[1]
 import torch
 from kvpress_b200 import native
 import bench
@@ -16,8 +18,7 @@ def timeit(fn, n=10):
         a, b = (K, V) if i % 2 == 0 else (K2, V2)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(); fn(a, b); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e) * 1e3)
-    ts.sort(); return ts[0], ts[len(ts) // 2]
+    ts.sort(); return round(ts[0], 1), round(ts[len(ts) // 2], 1)
+print(os.environ.get("KVPRESS_B200_LIB", "default lib"))
 print("score, cov, vnorm   :", timeit(lambda k, v: native.expected_attention_score(k, v, extra["mu"], extra["cov"], 0.0, 4, True)))
 print("score, cov, no vnorm:", timeit(lambda k, v: native.expected_attention_score(k, v, extra["mu"], extra["cov"], 0.0, 4, False)))
-print("score, no cov, vnorm:", timeit(lambda k, v: native.expected_attention_score(k, v, extra["mu"], None, 0.0, 4, True)))
-print("knorm score         :", timeit(lambda k, v: native.knorm_score(v)))
