@@ -349,18 +349,19 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     s_red[((warp - 4) * 2 + q) * 2 + 1] = z;
                 }
             }
-        } else if (warp >= 12) {
+        } else if (warp >= 12 || warp == 2 || warp == 3) {
             // ===== V norms for the same tiles: software-pipelined streaming loads. Each warp-wide load
             // covers 2 rows (16 lanes x 16 B per row); a "group" is 8 such loads (16 rows per warp,
             // 64 rows per 4 warps); the loads of group i+1 are in flight while group i is reduced, and
             // the 4-level shuffle reductions of the 8 rows of a group run in lockstep (ILP 8). =====
             if (use_vnorm) {
                 EA_T0();
-                const int vw = warp - 12;
+                constexpr int NVW = 6;                               // V-norm warps: 2, 3, 12..15
+                const int vw = warp >= 12 ? warp - 10 : warp - 2;
                 const int sub = lane & 15, rsel = lane >> 4;
                 constexpr int nvec = D / 8;
                 constexpr int GRP = 6;                               // loads per lane per group
-                constexpr int ROWS_PER_GRP = GRP * 2 * 4;            // 64 rows per group (4 warps)
+                constexpr int ROWS_PER_GRP = GRP * 2 * NVW;          // rows per group over all V warps
                 const T* vbase = V + (int64_t)b * vs.b + (int64_t)h * vs.h + sub * 8;
                 const uint64_t pol = l2_policy_evict_first();
                 const int s_lo = t_begin * kEaTile;
@@ -371,7 +372,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                 auto issue = [&](int4 (&dst)[GRP], int grp) {
 #pragma unroll
                     for (int u = 0; u < GRP; ++u) {
-                        const int s = s_lo + grp * ROWS_PER_GRP + u * 8 + vw * 2 + rsel;
+                        const int s = s_lo + grp * ROWS_PER_GRP + u * (2 * NVW) + vw * 2 + rsel;
                         dst[u] = make_int4(0, 0, 0, 0);
 #ifdef KVP_EA_VPLAIN
                         if (s < s_hi && sub < nvec) dst[u] = ldg_plain(vbase + (int64_t)s * vs.s);
@@ -402,7 +403,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     }
 #pragma unroll
                     for (int u = 0; u < GRP; ++u) {
-                        const int s = s_lo + grp * ROWS_PER_GRP + u * 8 + vw * 2 + rsel;
+                        const int s = s_lo + grp * ROWS_PER_GRP + u * (2 * NVW) + vw * 2 + rsel;
                         if (sub == 0 && s < s_hi) sc.vnorm[(size_t)row * S_pad + s] = sqrtf(ss[u]);
                     }
                 };

@@ -220,7 +220,6 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
                         umma::tmem_ld_wait();
                         if (cc + 1 < kBufCols / 16) umma::tmem_ld16(tbase + (cc + 1) * 16, y[(cc + 1) & 1]);
                         float v[16];
-                        float cmax = -INFINITY;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             v[j] = __uint_as_float(y[cc & 1][j]) * c;
@@ -228,14 +227,25 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
                                 const int pos = key0 + cc * 16 + j;
                                 if (pos > limit || pos >= S) v[j] = -INFINITY;
                             }
-                            cmax = fmaxf(cmax, v[j]);
                         }
+                        // tree max (depth 4) instead of a 16-long dependent chain
+                        float m8[8], m4[4];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) m8[j] = fmaxf(v[j], v[j + 8]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) m4[j] = fmaxf(m8[j], m8[j + 4]);
+                        const float cmax = fmaxf(fmaxf(m4[0], m4[2]), fmaxf(m4[1], m4[3]));
                         const float m_new = fmaxf(m, cmax);
                         if (m_new > -INFINITY) {
-                            float acc = 0.f;
+                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four independent sum chains
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) acc += fast_exp2(v[j] - m_new);
-                            z = z * fast_exp2(m - m_new) + acc;
+                            for (int j = 0; j < 16; j += 4) {
+                                a0 += fast_exp2(v[j] - m_new);
+                                a1 += fast_exp2(v[j + 1] - m_new);
+                                a2 += fast_exp2(v[j + 2] - m_new);
+                                a3 += fast_exp2(v[j + 3] - m_new);
+                            }
+                            z = z * fast_exp2(m - m_new) + ((a0 + a1) + (a2 + a3));
                             m = m_new;
                         }
                     }
