@@ -60,7 +60,7 @@ static WsLayout layout(const Dims& d, int scorer, int window) {
     L.S_pad = L.n_tiles * kTile;
     size_t off = 0;
     L.hist_off = off;  // hist_hi then hist_lo, zeroed together by one memset node
-    L.hist_bytes = ((size_t)d.R * 256 * 2 + (size_t)d.R * 2 + 64) * sizeof(uint32_t);
+    L.hist_bytes = ((size_t)d.R * 256 * 2 + (size_t)d.R * 3 + 64) * sizeof(uint32_t);
     off = align_up(off + L.hist_bytes, 256);
     L.keys_off = off;
     off = align_up(off + (size_t)d.R * L.S_pad * sizeof(uint16_t), 256);
@@ -147,8 +147,8 @@ int kvp_launches_per_compress(const kvp_problem* p, int scorer, int* launches_ou
     if (!p || !launches_out) return KVP_ERR_NULL_POINTER;
     switch (scorer) {
         case KVP_SCORER_STREAMING: *launches_out = 1; break;
-        case KVP_SCORER_GENERIC:
-        case KVP_SCORER_KNORM: *launches_out = 3; break;  // memset, score, select+compact
+        case KVP_SCORER_GENERIC: *launches_out = 3; break;  // memset, keys, select+compact
+        case KVP_SCORER_KNORM: *launches_out = 2; break;  // memset, fused score+select+compact
         case KVP_SCORER_SNAPKV: *launches_out = 6; break;
         case KVP_SCORER_EXPECTED_ATTENTION: *launches_out = 4; break;  // memset, logits, finalize, select+compact
         default: return KVP_ERR_BAD_ARGUMENT;
@@ -190,9 +190,14 @@ int kvp_knorm_compress(const kvp_problem* p, const void* K, const void* V, void*
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaMemsetAsync(ws.hist_hi, 0, L.hist_bytes, st);
     if (e != cudaSuccess) return fail_cuda(e);
-    e = launch_knorm_score(d, p->dtype, K, ws, scores_out, true, st);
-    if (e != cudaSuccess) return fail_cuda(e);
-    return select_and_compact(d, K, V, K_out, V_out, idx_out, ws, st);
+    // score + select + compact as one persistent kernel (row-pipelined so K is re-read from L2)
+    e = launch_knorm_fused(d, p->dtype, K, V, K_out, V_out, idx_out, scores_out, ws, st);
+    if (e == cudaErrorNotSupported) {  // > 2^31 work items: three-kernel path
+        e = launch_knorm_score(d, p->dtype, K, ws, scores_out, true, st);
+        if (e != cudaSuccess) return fail_cuda(e);
+        return select_and_compact(d, K, V, K_out, V_out, idx_out, ws, st);
+    }
+    return e == cudaSuccess ? KVP_OK : fail_cuda(e);
 }
 
 // ---- StreamingLLM --------------------------------------------------------------------------------

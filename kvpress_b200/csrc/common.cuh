@@ -17,7 +17,8 @@ constexpr int kSfxStride = 264;     // u16 per tile record: sfx[0..256], gt_hi a
 constexpr uint16_t kForcedKey = 0xFFFFu;  // ordered key of a forced-keep position
 constexpr int kScoreChunkGeneric = 256;   // positions per CTA of the plain streaming score kernels
 // counters[] layout: [0] ticket, [1, 1+R) refine done, [1+R, 1+2R) row ready, then the slot below:
-// order-preserving uint image of the largest valid score (for the reference's max+1 sentinel)
+// order-preserving uint image of the largest valid score (for the reference's max+1 sentinel);
+// [2+2R, 2+3R) score items done per row (fused Knorm kernel)
 __host__ __device__ constexpr int kCounterMaxSlot(int R) { return 1 + 2 * R; }
 
 struct Strides3 {
@@ -214,6 +215,9 @@ __device__ __forceinline__ void flush_chunk_keys(const uint16_t* skeys, const ui
 // ---- launchers implemented in the .cu files (host, C++ linkage) -------------------------------
 cudaError_t launch_knorm_score(const Dims& d, int dtype, const void* K, const Workspace& ws,
                                void* scores_out, bool want_keys, cudaStream_t st);
+cudaError_t launch_knorm_fused(const Dims& d, int dtype, const void* K, const void* V, void* K_out,
+                               void* V_out, int32_t* idx_out, void* scores_out, const Workspace& ws,
+                               cudaStream_t st);
 cudaError_t launch_keys_from_scores(const Dims& d, int dtype, const void* scores, int64_t sb, int64_t sh,
                                     const Workspace& ws, cudaStream_t st);
 cudaError_t launch_select_compact(const Dims& d, const void* K, const void* V, void* K_out,

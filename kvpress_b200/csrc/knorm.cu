@@ -7,10 +7,9 @@
 // the 16-bit ordered keys in shared memory, writes them coalesced and adds the tile's
 // histogram of (key >> 8) to the row histogram the select stage starts from.
 #include "common.cuh"
+#include "knorm_chunk.cuh"
 
 namespace kvp {
-
-constexpr int kScoreChunk = 256;  // positions per score CTA (finer than kTile: better balance)
 
 template <typename T, int LPR>
 __global__ void __launch_bounds__(kTileThreads)
@@ -19,58 +18,9 @@ knorm_score_kernel(const T* __restrict__ K, Strides3 ks, int H, int S, int D, Wo
     __shared__ uint16_t skeys[kScoreChunk];
     __shared__ uint16_t sscores[kScoreChunk];
     __shared__ uint32_t shist[256];
-
-    const int chunk = blockIdx.x;
-    const int row = blockIdx.y;
-    const int b = row / H, h = row % H;
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int chunk = blockIdx.x, row = blockIdx.y, tid = threadIdx.x;
     shist[tid] = 0;  // kTileThreads == 256
-
-    constexpr int RPW = 32 / LPR;                                   // rows per warp-wide load
-    constexpr int TOK_PER_WARP = kScoreChunk / (kTileThreads / 32);  // 32
-    constexpr int ITERS = TOK_PER_WARP / RPW;
-    constexpr int U = (ITERS < 8) ? ITERS : 8;  // independent 16-byte loads in flight per lane
-    static_assert(ITERS % U == 0, "unroll must divide the iteration count");
-
-    const int sub = lane % LPR;   // which 16-byte piece of the row
-    const int rsel = lane / LPR;  // which row of the RPW rows
-    const int nvec = D >> 3;      // 16-byte pieces per row
-    const T* base = K + (int64_t)b * ks.b + (int64_t)h * ks.h + (int64_t)sub * 8;
-    const int s_warp = chunk * kScoreChunk + warp * TOK_PER_WARP;
-
-#pragma unroll 1
-    for (int it = 0; it < ITERS; it += U) {
-        int4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int s = s_warp + (it + u) * RPW + rsel;
-            v[u] = make_int4(0, 0, 0, 0);
-            if (s < S && sub < nvec) v[u] = ldg_plain(base + (int64_t)s * ks.s);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t w[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z,
-                                   (uint32_t)v[u].w};
-            float ss = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = F16Traits<T>::unpack2(w[j]);
-                ss = fmaf(f.x, f.x, ss);
-                ss = fmaf(f.y, f.y, ss);
-            }
-#pragma unroll
-            for (int off = LPR / 2; off >= 1; off >>= 1)
-                ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
-            if (sub == 0) {
-                const int sl = warp * TOK_PER_WARP + (it + u) * RPW + rsel;
-                // -sqrt(ss) rounded once to the storage dtype (negation is exact)
-                const uint16_t bits = F16Traits<T>::from_float(sqrtf(ss)) ^ 0x8000u;
-                sscores[sl] = bits;
-                skeys[sl] = ordered_key16(bits, F16Traits<T>::kInfBits);
-            }
-        }
-    }
+    knorm_score_chunk<T, LPR>(K, ks, row / H, row % H, chunk, S, D, skeys, sscores);
     __syncthreads();
     const int s_begin = chunk * kScoreChunk;
     if (want_keys) {

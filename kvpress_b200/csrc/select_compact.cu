@@ -16,6 +16,7 @@
 // Tiles are visited in REVERSE order of the score stage so the K rows touched last (still in the
 // 126 MB L2) are re-read first.
 #include "common.cuh"
+#include "knorm_chunk.cuh"
 
 namespace kvp {
 
@@ -143,7 +144,7 @@ __device__ __forceinline__ void scan_row(SelectSmem& sm, int row, int n_kept, co
 __device__ __forceinline__ void refine_item(SelectSmem& sm, int row, int group, int n_groups, int S,
                                             int n_kept, const Workspace& ws) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    sm.hist[tid] = ws.hist_hi[(size_t)row * 256 + tid];
+    sm.hist[tid] = __ldcg(&ws.hist_hi[(size_t)row * 256 + tid]);  // written by other CTAs' atomics
     __syncthreads();
     if (warp == 0) {
         int b1;
@@ -347,6 +348,141 @@ cudaError_t launch_select_compact(const Dims& d, const void* K, const void* V, v
         static_cast<const char*>(K), static_cast<const char*>(V), d.ks, d.vs,
         static_cast<char*>(K_out), static_cast<char*>(V_out), idx_out, d.H, d.S, d.D, d.n_kept, ws);
     return cudaPeekAtLastError();
+}
+
+// ---- KnormPress: score + select + compact in ONE persistent kernel ---------------------------------
+// Work items of three kinds share one ticket queue: S(row, chunk) scores 256 positions and adds to the
+// row histogram; A(row, group) is the refine item (waits until all S items of its row are done);
+// B(row, tile) is the compact item (waits for the row's ready flag). The queue is laid out in blocks
+//     block p = [ A(p-1) | S(p,0) B(p-2,0) S(p,1) B(p-2,1) ... ]
+// so that while row p is being scored (pure HBM reads), row p-2 is compacted: its K rows were read two
+// blocks ago (~2 x 32 MiB of traffic at 128k) and are re-read from the 126 MB L2 instead of HBM, its V
+// reads and all stores are L2-evict-first. Every item only waits on items that precede it in the
+// queue, and S items never wait, so the kernel cannot deadlock for any grid size.
+struct FusedItem {
+    int kind;  // 0 = score, 1 = refine, 2 = compact, -1 = done
+    int row, idx;
+};
+
+__device__ __forceinline__ FusedItem decode_fused_item(long long item, int R, int nT, int nA) {
+    FusedItem it = {-1, 0, 0};
+    for (int p = 0; p <= R + 1; ++p) {
+        // closed form over the identical middle blocks
+        if (p == 2 && R > 2) {
+            const long long full = (long long)nA + 2ll * nT;
+            const long long skip = item / full;
+            const long long n_mid = R - 2;
+            const long long take = skip < n_mid ? skip : n_mid;
+            item -= take * full;
+            p += (int)take;
+        }
+        const int a = (p >= 1 && p <= R) ? nA : 0;
+        const int s = (p < R) ? nT : 0;
+        const int b = (p >= 2) ? nT : 0;
+        const long long size = (long long)a + s + b;
+        if (item >= size) {
+            item -= size;
+            continue;
+        }
+        if (item < a) {
+            it.kind = 1; it.row = p - 1; it.idx = (int)item;
+            return it;
+        }
+        const int j = (int)(item - a);
+        if (s && b) {
+            if (j & 1) { it.kind = 2; it.row = p - 2; it.idx = j >> 1; }
+            else       { it.kind = 0; it.row = p;     it.idx = j >> 1; }
+        } else if (s) {
+            it.kind = 0; it.row = p; it.idx = j;
+        } else {
+            it.kind = 2; it.row = p - 2; it.idx = j;
+        }
+        return it;
+    }
+    return it;
+}
+
+__device__ __forceinline__ void spin_until(const uint32_t* counter, uint32_t need) {
+    const volatile uint32_t* flag = counter;
+    uint32_t spins = 0;
+    while (*flag < need) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) __trap();  // a bug must not hang the GPU
+    }
+    __threadfence();
+}
+
+template <typename T, int LPR>
+__global__ void __launch_bounds__(kTileThreads, 3)
+knorm_fused_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks, Strides3 vs,
+                   char* __restrict__ K_out, char* __restrict__ V_out, int32_t* __restrict__ idx_out,
+                   uint16_t* __restrict__ scores_out, int H, int S, int D, int n_kept, Workspace ws) {
+    __shared__ SelectSmem sm;
+    const int R = ws.R, nT = ws.n_tiles;
+    const int nA = (nT + kGroupTiles - 1) / kGroupTiles;
+    const long long total = (long long)R * (2ll * nT + nA);
+    uint32_t* score_done = ws.counters + kCounterMaxSlot(R) + 1;  // [R]
+    uint16_t* skeys = reinterpret_cast<uint16_t*>(sm.list);       // 2 x 256 u16 alias the 1 KB list
+    uint16_t* sscores = skeys + kScoreChunk;
+    const int tid = threadIdx.x;
+    while (true) {
+        __syncthreads();  // previous item's shared state is dead
+        if (tid == 0) sm.item = (int)atomicAdd(&ws.counters[0], 1u);
+        __syncthreads();
+        const long long item = (long long)(uint32_t)sm.item;
+        if (item >= total) break;
+        const FusedItem it = decode_fused_item(item, R, nT, nA);
+        if (it.kind == 0) {
+            sm.hist[tid] = 0;
+            knorm_score_chunk<T, LPR>(K, ks, it.row / H, it.row % H, it.idx, S, D, skeys, sscores);
+            __syncthreads();
+            flush_chunk_keys<1>(skeys, sscores, sm.hist, it.row, it.idx * kScoreChunk, S, ws, scores_out);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicAdd(&score_done[it.row], 1u);
+        } else if (it.kind == 1) {
+            if (tid == 0) spin_until(&score_done[it.row], (uint32_t)nT);
+            __syncthreads();
+            refine_item(sm, it.row, it.idx, nA, S, n_kept, ws);
+        } else {
+            compact_item(sm, it.row, it.idx, reinterpret_cast<const char*>(K),
+                         reinterpret_cast<const char*>(V), ks, vs, K_out, V_out, idx_out, H, S, D, n_kept,
+                         ws);
+        }
+    }
+}
+
+template <typename T>
+static cudaError_t launch_knorm_fused_t(const Dims& d, const void* K, const void* V, void* K_out,
+                                        void* V_out, int32_t* idx_out, void* scores_out,
+                                        const Workspace& ws, cudaStream_t st) {
+    const int nA = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
+    const long long total = (long long)d.R * (2ll * ws.n_tiles + nA);
+    if (total > 0x7FFFFFFFll) return cudaErrorNotSupported;
+    const int nvec = d.D / 8;
+#define KVP_LAUNCH_FUSED(LPR)                                                                         \
+    do {                                                                                              \
+        auto kern = knorm_fused_kernel<T, LPR>;                                                       \
+        const int grid = persistent_grid(reinterpret_cast<const void*>(kern), kTileThreads, (int)total); \
+        kern<<<grid, kTileThreads, 0, st>>>(static_cast<const T*>(K), static_cast<const T*>(V), d.ks,  \
+                                            d.vs, static_cast<char*>(K_out), static_cast<char*>(V_out), \
+                                            idx_out, static_cast<uint16_t*>(scores_out), d.H, d.S, d.D, \
+                                            d.n_kept, ws);                                            \
+    } while (0)
+    if (nvec <= 4) KVP_LAUNCH_FUSED(4);
+    else if (nvec <= 8) KVP_LAUNCH_FUSED(8);
+    else if (nvec <= 16) KVP_LAUNCH_FUSED(16);
+    else KVP_LAUNCH_FUSED(32);
+#undef KVP_LAUNCH_FUSED
+    return cudaPeekAtLastError();
+}
+
+cudaError_t launch_knorm_fused(const Dims& d, int dtype, const void* K, const void* V, void* K_out,
+                               void* V_out, int32_t* idx_out, void* scores_out, const Workspace& ws,
+                               cudaStream_t st) {
+    if (dtype == KVP_BF16)
+        return launch_knorm_fused_t<__nv_bfloat16>(d, K, V, K_out, V_out, idx_out, scores_out, ws, st);
+    return launch_knorm_fused_t<__half>(d, K, V, K_out, V_out, idx_out, scores_out, ws, st);
 }
 
 // ---- StreamingLLM: the answer is two ranges, no scores needed --------------------------------
