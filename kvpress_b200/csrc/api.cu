@@ -148,8 +148,10 @@ int kvp_launches_per_compress(const kvp_problem* p, int scorer, int* launches_ou
     switch (scorer) {
         case KVP_SCORER_STREAMING: *launches_out = 1; break;
         case KVP_SCORER_GENERIC: *launches_out = 3; break;  // memset, keys, select+compact
-        case KVP_SCORER_KNORM: *launches_out = 2; break;  // memset, fused score+select+compact
-        case KVP_SCORER_SNAPKV: *launches_out = 6; break;
+        case KVP_SCORER_KNORM:  // memset + (fused | score, select+compact)
+            *launches_out = ((size_t)p->B * p->Hkv * p->S * p->D * 2 <= ((size_t)32 << 20)) ? 2 : 3;
+            break;
+        case KVP_SCORER_SNAPKV: *launches_out = 7; break;  // memset, stats, combine, memset, colsum, finalize, select+compact
         case KVP_SCORER_EXPECTED_ATTENTION: *launches_out = 4; break;  // memset, logits, finalize, select+compact
         default: return KVP_ERR_BAD_ARGUMENT;
     }
@@ -190,14 +192,17 @@ int kvp_knorm_compress(const kvp_problem* p, const void* K, const void* V, void*
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaMemsetAsync(ws.hist_hi, 0, L.hist_bytes, st);
     if (e != cudaSuccess) return fail_cuda(e);
-    // score + select + compact as one persistent kernel (row-pipelined so K is re-read from L2)
-    e = launch_knorm_fused(d, p->dtype, K, V, K_out, V_out, idx_out, scores_out, ws, st);
-    if (e == cudaErrorNotSupported) {  // > 2^31 work items: three-kernel path
-        e = launch_knorm_score(d, p->dtype, K, ws, scores_out, true, st);
-        if (e != cudaSuccess) return fail_cuda(e);
-        return select_and_compact(d, K, V, K_out, V_out, idx_out, ws, st);
+    // Small caches (DecodingPress compactions) are launch-latency-bound: one persistent kernel does
+    // score + select + compact. Large caches measured faster as two kernels (the fused kernel's mixed
+    // read/write item stream costs more HBM efficiency than the saved launch; K re-reads miss L2 anyway).
+    const size_t k_bytes = (size_t)d.R * d.S * d.D * 2;
+    if (k_bytes <= ((size_t)32 << 20)) {
+        e = launch_knorm_fused(d, p->dtype, K, V, K_out, V_out, idx_out, scores_out, ws, st);
+        if (e != cudaErrorNotSupported) return e == cudaSuccess ? KVP_OK : fail_cuda(e);
     }
-    return e == cudaSuccess ? KVP_OK : fail_cuda(e);
+    e = launch_knorm_score(d, p->dtype, K, ws, scores_out, true, st);
+    if (e != cudaSuccess) return fail_cuda(e);
+    return select_and_compact(d, K, V, K_out, V_out, idx_out, ws, st);
 }
 
 // ---- StreamingLLM --------------------------------------------------------------------------------

@@ -15,6 +15,7 @@ constexpr int kTile = 256;          // positions per select/compact tile (one pe
 constexpr int kTileThreads = 256;
 constexpr int kSfxStride = 264;     // u16 per tile record: sfx[0..256], gt_hi at [257], padding
 constexpr uint16_t kForcedKey = 0xFFFFu;  // ordered key of a forced-keep position
+constexpr int kFinalizeTiles = 4;          // 256-position tiles per CTA of the finalize kernels
 constexpr int kScoreChunkGeneric = 256;   // positions per CTA of the plain streaming score kernels
 // counters[] layout: [0] ticket, [1, 1+R) refine done, [1+R, 1+2R) row ready, then the slot below:
 // order-preserving uint image of the largest valid score (for the reference's max+1 sentinel);
@@ -167,12 +168,21 @@ __device__ __forceinline__ void warp_suffix_find(const uint32_t* hist, uint32_t 
     above = __shfl_sync(0xFFFFFFFFu, my_above, first);
 }
 
+// Adds a CTA's shared-memory histogram to the row histogram (call after a __syncthreads()).
+__device__ __forceinline__ void flush_row_hist(const uint32_t* shist, int row, const Workspace& ws) {
+    const int tid = threadIdx.x;
+    if (tid < 256) {
+        const uint32_t c = shist[tid];
+        if (c) atomicAdd(&ws.hist_hi[(size_t)row * 256 + tid], c);
+    }
+}
+
 // Common tail of every score kernel: KPT keys (and optionally scores) per thread staged in shared
 // memory for a chunk of KPT*blockDim positions starting at s_begin -> coalesced global writes + row
 // histogram of (key >> 8). Shared-memory atomics are warp-aggregated with match.any so heavily tied
 // scores (bf16 norms take ~100 distinct values) do not serialise on one address.
 // Call with all threads of a 256-thread CTA after a __syncthreads(); shist must be zeroed.
-template <int KPT>
+template <int KPT, bool kFlushHist = true>
 __device__ __forceinline__ void flush_chunk_keys(const uint16_t* skeys, const uint16_t* sscores,
                                                  uint32_t* shist, int row, int s_begin, int S,
                                                  const Workspace& ws, uint16_t* scores_out) {
@@ -205,10 +215,9 @@ __device__ __forceinline__ void flush_chunk_keys(const uint16_t* skeys, const ui
         const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
         if (bin < 256u && lane == (__ffs(peers) - 1)) atomicAdd(&shist[bin], __popc(peers));
     }
-    __syncthreads();
-    if (tid < 256) {
-        const uint32_t c = shist[tid];
-        if (c) atomicAdd(&ws.hist_hi[(size_t)row * 256 + tid], c);
+    if (kFlushHist) {
+        __syncthreads();
+        flush_row_hist(shist, row, ws);
     }
 }
 

@@ -569,26 +569,32 @@ ea_finalize_kernel(int G, int S, int n_sink, int use_vnorm, float eps, int n_par
         }
     }
     __syncthreads();
-    const int s = tile * kTile + tid;
-    float score = 0.f;
-    uint16_t bits = 0, key = 0;
     float fmax_valid = -INFINITY;
-    if (s < S) {
-        if (s < n_sink) {
-            key = kForcedKey;
-        } else {
-            float p = 0.f;
-            for (int g = 0; g < G; ++g)
-                p += __expf(sc.logits[((size_t)row * G + g) * ws.S_pad + s] - s_m[g]) * s_iz[g];
-            p *= (1.0f / (float)G);
-            score = use_vnorm ? (p + eps) * sc.vnorm[(size_t)row * ws.S_pad + s] : p;
-            bits = F16Traits<T>::from_float(score);
-            key = ordered_key16(bits, F16Traits<T>::kInfBits);
-            fmax_valid = F16Traits<T>::to_float(bits);
+    for (int sub = 0; sub < kFinalizeTiles; ++sub) {
+        const int t = tile * kFinalizeTiles + sub;
+        if (t >= ws.n_tiles) break;
+        const int s = t * kTile + tid;
+        uint16_t bits = 0, key = 0;
+        if (s < S) {
+            if (s < n_sink) {
+                key = kForcedKey;
+            } else {
+                float p = 0.f;
+                for (int g = 0; g < G; ++g)
+                    p += __expf(sc.logits[((size_t)row * G + g) * ws.S_pad + s] - s_m[g]) * s_iz[g];
+                p *= (1.0f / (float)G);
+                const float score = use_vnorm ? (p + eps) * sc.vnorm[(size_t)row * ws.S_pad + s] : p;
+                bits = F16Traits<T>::from_float(score);
+                key = ordered_key16(bits, F16Traits<T>::kInfBits);
+                fmax_valid = fmaxf(fmax_valid, F16Traits<T>::to_float(bits));
+            }
         }
+        __syncthreads();  // previous sub-tile's staging buffers are free
+        skeys[tid] = key;
+        sscores[tid] = bits;
+        __syncthreads();
+        flush_chunk_keys<1, false>(skeys, sscores, shist, row, t * kTile, S, ws, scores_out);
     }
-    skeys[tid] = key;
-    sscores[tid] = bits;
     // max over valid scores of the whole tensor (for the reference's max+1 sentinel)
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1)
@@ -605,7 +611,7 @@ ea_finalize_kernel(int G, int S, int n_sink, int use_vnorm, float eps, int n_par
             atomicMax(&ws.counters[kCounterMaxSlot(ws.R)], ord);
         }
     }
-    flush_chunk_keys<1>(skeys, sscores, shist, row, tile * kTile, S, ws, scores_out);
+    flush_row_hist(shist, row, ws);
 }
 
 // scores_out[..., lo:hi] = round(max_valid_score + 1) — the value the reference pads with
@@ -713,7 +719,7 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
         e = cudaPeekAtLastError();
     }
     if (e != cudaSuccess) return e;
-    dim3 grid2(ws.n_tiles, d.R);
+    dim3 grid2((ws.n_tiles + kFinalizeTiles - 1) / kFinalizeTiles, d.R);
     ea_finalize_kernel<T><<<grid2, kTileThreads, 0, st>>>(G, d.S, n_sink, use_vnorm, eps, n_parts, sc, ws,
                                                           static_cast<uint16_t*>(scores_out));
     e = cudaPeekAtLastError();

@@ -26,8 +26,8 @@
 namespace kvp {
 
 constexpr int kSnTile = 128;
-constexpr int kSnThreads = 384;  // 12 warps: TMA, MMA, TMEM-alloc, spare, 2 x 4 epilogue
-constexpr int kSnMaxParts = 160;
+constexpr int kSnThreads = 640;  // 20 warps: TMA, MMA, TMEM-alloc, spare, 4 x 4 epilogue (2 warpgroups per TMEM buffer)
+constexpr int kSnMaxParts = 640;
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2, 2 ulp; exp2(-inf) = 0
@@ -121,7 +121,7 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
             umma::mbar_init(&k_full[i], 1);
             umma::mbar_init(&k_empty[i], 1);  // MMA commit only: the epilogue never reads K from smem
             umma::mbar_init(&t_full[i], 1);
-            umma::mbar_init(&t_empty[i], 4);
+            umma::mbar_init(&t_empty[i], 8);  // two warpgroups (column halves) drain each buffer
         }
         umma::mbar_init(q_full, 1);
         umma::mbar_fence_init();
@@ -188,10 +188,14 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
             }
             ++q_it;
         } else if (warp >= 4) {
-            // ===== epilogue: warpgroup wg drains TMEM buffer wg; thread = query row of the 128-block =====
-            const int wg = (warp - 4) >> 2;
+            // ===== epilogue: four warpgroups; warpgroup (buf, ch) drains column half ch of TMEM buffer buf;
+            // thread = query row of the 128-block =====
+            const int wgi = (warp - 4) >> 2;
+            const int wg = wgi & 1;   // TMEM buffer
+            const int ch = wgi >> 1;  // column half of the 128-key tile
             const int ew = warp & 3;
             const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+            constexpr int kHalfCols = kBufCols / 2;  // 64 keys per warpgroup
             // each warpgroup may serve several 128-row blocks of Q (NQP = 512 -> two each)
             float run_m[(kQHalves + 1) / 2], run_z[(kQHalves + 1) / 2];
 #pragma unroll
@@ -200,8 +204,8 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
                 run_z[i] = 0.f;
             }
             for (int t = t_begin; t < t_end; ++t) {
-                const int key0 = t * kSnTile;
-                const bool interior = (key0 + kSnTile) <= (S - window);  // no masking, all keys valid
+                const int key0 = t * kSnTile + ch * kHalfCols;
+                const bool interior = (key0 + kHalfCols) <= (S - window);  // no masking, all keys valid
 #pragma unroll
                 for (int qh = 0; qh < kQHalves; ++qh, ++h_it) {
                     const int buf = h_it & 1;
@@ -211,14 +215,14 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
                     const int limit = (S - window) + (r % window);  // last visible key position
                     umma::mbar_wait(&t_full[buf], (h_it >> 1) & 1);
                     umma::fence_after_sync();
-                    const uint32_t tbase = tmem + lane_base + buf * kBufCols;
+                    const uint32_t tbase = tmem + lane_base + buf * kBufCols + ch * kHalfCols;
                     uint32_t y[2][16];
                     umma::tmem_ld16(tbase, y[0]);
                     float m = run_m[slot], z = run_z[slot];
 #pragma unroll
-                    for (int cc = 0; cc < kBufCols / 16; ++cc) {
+                    for (int cc = 0; cc < kHalfCols / 16; ++cc) {
                         umma::tmem_ld_wait();
-                        if (cc + 1 < kBufCols / 16) umma::tmem_ld16(tbase + (cc + 1) * 16, y[(cc + 1) & 1]);
+                        if (cc + 1 < kHalfCols / 16) umma::tmem_ld16(tbase + (cc + 1) * 16, y[(cc + 1) & 1]);
                         float v[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -258,14 +262,12 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
             }
 #pragma unroll
             for (int qh = 0; qh < kQHalves; ++qh) {
-                if ((qh & 1) != wg && kQHalves > 1) continue;
-                if (kQHalves == 1 && wg != 0) {
-                    // single 128-row block: both warpgroups alternate tiles and hold partial stats
-                }
+                if (kQHalves > 1 && (qh & 1) != wg) continue;
                 const int r = qh * 128 + ew * 32 + lane;
                 if (r < NQ) {
-                    // with one Q block the two warpgroups saw alternate tiles: store both, parts doubled
-                    const int p_idx = (kQHalves == 1) ? (part * 2 + wg) : part;
+                    // one Q block: both buffers (alternate tiles) x both column halves hold partial stats;
+                    // several Q blocks: the block's buffer is fixed, two column halves
+                    const int p_idx = (kQHalves == 1) ? (part * 4 + wg * 2 + ch) : (part * 2 + ch);
                     sc.partial[((size_t)row * NQ + r) * n_parts + p_idx] =
                         make_float2(run_m[qh >> 1], run_z[qh >> 1]);
                 }
@@ -331,7 +333,7 @@ snap_colsum_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_consta
             umma::mbar_init(&k_full[i], 1);
             umma::mbar_init(&k_empty[i], 1);
             umma::mbar_init(&t_full[i], 1);
-            umma::mbar_init(&t_empty[i], 4);
+            umma::mbar_init(&t_empty[i], 8);
         }
         umma::mbar_init(q_full, 1);
         umma::mbar_fence_init();
@@ -423,10 +425,14 @@ snap_colsum_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_consta
             }
             ++q_it;
         } else if (warp >= 4) {
-            // ===== epilogue: thread = key; sums exp2(c * D[key, r]) over the query rows r =====
-            const int wg = (warp - 4) >> 2;
+            // ===== epilogue: thread = key; warpgroup (buf, ch) sums exp2(c * D[key, r]) over column half ch
+            // (query rows) of TMEM buffer buf; the halves meet in global memory with one atomicAdd each =====
+            const int wgi = (warp - 4) >> 2;
+            const int wg = wgi & 1;
+            const int ch = wgi >> 1;
             const int ew = warp & 3;
             const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+            constexpr int kHalfCols = kNPer / 2;
             for (int t = t_begin; t < t_end; ++t) {
                 const int pos = t * kSnTile + ew * 32 + lane;
                 float total = 0.f;
@@ -438,31 +444,34 @@ snap_colsum_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_consta
                     mine = true;
                     umma::mbar_wait(&t_full[buf], (h_it >> 1) & 1);
                     umma::fence_after_sync();
-                    const uint32_t tbase = tmem + lane_base + buf * kBufCols;
-                    const int n_cols = min(kNPer, NQ - nc * kNPer);  // real query rows in this chunk
-                    uint32_t y0[16], y1[16];
-                    umma::tmem_ld16(tbase, y0);
+                    const uint32_t tbase = tmem + lane_base + buf * kBufCols + ch * kHalfCols;
+                    // real query rows in this warpgroup's column half
+                    const int n_cols = max(0, min(kHalfCols, NQ - nc * kNPer - ch * kHalfCols));
                     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                    auto accumulate = [&](const uint32_t (&yy)[16]) {
+                    if (n_cols > 0) {
+                        uint32_t y0[16], y1[16];
+                        umma::tmem_ld16(tbase, y0);
+                        auto accumulate = [&](const uint32_t (&yy)[16]) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            a0 += fast_exp2(__uint_as_float(yy[j]) * c);
-                            a1 += fast_exp2(__uint_as_float(yy[j + 1]) * c);
-                            a2 += fast_exp2(__uint_as_float(yy[j + 2]) * c);
-                            a3 += fast_exp2(__uint_as_float(yy[j + 3]) * c);
-                        }
-                    };
-                    // two 16-column chunks per iteration so both register buffers are static
+                            for (int j = 0; j < 16; j += 4) {
+                                a0 += fast_exp2(__uint_as_float(yy[j]) * c);
+                                a1 += fast_exp2(__uint_as_float(yy[j + 1]) * c);
+                                a2 += fast_exp2(__uint_as_float(yy[j + 2]) * c);
+                                a3 += fast_exp2(__uint_as_float(yy[j + 3]) * c);
+                            }
+                        };
+                        // two 16-column chunks per iteration so both register buffers are static
 #pragma unroll 1
-                    for (int c0 = 0; c0 < n_cols; c0 += 32) {
-                        umma::tmem_ld_wait();
-                        const bool more1 = (c0 + 16) < n_cols;
-                        if (more1) umma::tmem_ld16(tbase + c0 + 16, y1);
-                        accumulate(y0);
-                        if (more1) {
+                        for (int c0 = 0; c0 < n_cols; c0 += 32) {
                             umma::tmem_ld_wait();
-                            if (c0 + 32 < n_cols) umma::tmem_ld16(tbase + c0 + 32, y0);
-                            accumulate(y1);
+                            const bool more1 = (c0 + 16) < n_cols;
+                            if (more1) umma::tmem_ld16(tbase + c0 + 16, y1);
+                            accumulate(y0);
+                            if (more1) {
+                                umma::tmem_ld_wait();
+                                if (c0 + 32 < n_cols) umma::tmem_ld16(tbase + c0 + 32, y0);
+                                accumulate(y1);
+                            }
                         }
                     }
                     total += (a0 + a1) + (a2 + a3);
@@ -470,10 +479,7 @@ snap_colsum_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_consta
                     __syncwarp();
                     if (lane == 0) umma::mbar_arrive(&t_empty[buf]);
                 }
-                if (mine && pos < S - window) {
-                    if (kNChunks == 1) sc.colsum[(size_t)row * S_pad + pos] = total;
-                    else atomicAdd(&sc.colsum[(size_t)row * S_pad + pos], total);  // two warpgroups, two halves
-                }
+                if (mine && pos < S - window) atomicAdd(&sc.colsum[(size_t)row * S_pad + pos], total);
             }
         }
     }
@@ -493,28 +499,35 @@ snap_finalize_kernel(int S, int window, int kernel_size, float inv_gw, SnapScrat
     __shared__ float s_max[8];
     const int tile = blockIdx.x, row = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     shist[tid] = 0;
-    const int s = tile * kTile + tid;
     const int n_scored = S - window;
-    uint16_t bits = 0, key = 0;
     float fmax_valid = -INFINITY;
-    if (s < S) {
-        if (s >= n_scored) {
-            key = kForcedKey;
-        } else {
-            const int half = kernel_size >> 1;
-            float acc = 0.f;
-            for (int o = -half; o <= half; ++o) {
-                const int j = s + o;
-                if (j >= 0 && j < n_scored) acc += sc.colsum[(size_t)row * ws.S_pad + j];
+    for (int sub = 0; sub < kFinalizeTiles; ++sub) {
+        const int t = tile * kFinalizeTiles + sub;
+        if (t >= ws.n_tiles) break;
+        const int s = t * kTile + tid;
+        uint16_t bits = 0, key = 0;
+        if (s < S) {
+            if (s >= n_scored) {
+                key = kForcedKey;
+            } else {
+                const int half = kernel_size >> 1;
+                float acc = 0.f;
+                for (int o = -half; o <= half; ++o) {
+                    const int j = s + o;
+                    if (j >= 0 && j < n_scored) acc += sc.colsum[(size_t)row * ws.S_pad + j];
+                }
+                const float score = acc * inv_gw / (float)kernel_size;  // count_include_pad: always / kernel
+                bits = F16Traits<T>::from_float(score);
+                key = ordered_key16(bits, F16Traits<T>::kInfBits);
+                fmax_valid = fmaxf(fmax_valid, F16Traits<T>::to_float(bits));
             }
-            const float score = acc * inv_gw / (float)kernel_size;  // count_include_pad: always / kernel
-            bits = F16Traits<T>::from_float(score);
-            key = ordered_key16(bits, F16Traits<T>::kInfBits);
-            fmax_valid = F16Traits<T>::to_float(bits);
         }
+        __syncthreads();
+        skeys[tid] = key;
+        sscores[tid] = bits;
+        __syncthreads();
+        flush_chunk_keys<1, false>(skeys, sscores, shist, row, t * kTile, S, ws, scores_out);
     }
-    skeys[tid] = key;
-    sscores[tid] = bits;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1)
         fmax_valid = fmaxf(fmax_valid, __shfl_xor_sync(0xFFFFFFFFu, fmax_valid, off));
@@ -528,7 +541,7 @@ snap_finalize_kernel(int S, int window, int kernel_size, float inv_gw, SnapScrat
             atomicMax(&ws.counters[kCounterMaxSlot(ws.R)], (u & 0x80000000u) ? ~u : (u | 0x80000000u));
         }
     }
-    flush_chunk_keys<1>(skeys, sscores, shist, row, tile * kTile, S, ws, scores_out);
+    flush_row_hist(shist, row, ws);
 }
 
 // ---- host launcher -----------------------------------------------------------------------------------------
@@ -550,11 +563,11 @@ static cudaError_t launch_snap_t(const Dims& d, int dtype, const void* K, const 
     int ctas_per_row = sm_count / d.R;
     if (ctas_per_row < 1) ctas_per_row = 1;
     if (ctas_per_row > n_tiles128) ctas_per_row = n_tiles128;
-    if (ctas_per_row > kSnMaxParts / 2) ctas_per_row = kSnMaxParts / 2;
+    if (ctas_per_row > kSnMaxParts / 4) ctas_per_row = kSnMaxParts / 4;
     int n_groups = sm_count / ctas_per_row;
     if (n_groups > d.R) n_groups = d.R;
     const int grid = n_groups * ctas_per_row;
-    const int n_parts = (NQP == 128) ? ctas_per_row * 2 : ctas_per_row;
+    const int n_parts = (NQP == 128) ? ctas_per_row * 4 : ctas_per_row * 2;
 
     CUtensorMap mapK, mapQ;
     {
@@ -590,14 +603,12 @@ static cudaError_t launch_snap_t(const Dims& d, int dtype, const void* K, const 
     const float inv_c = sqrtf((float)D) / kLog2e;
     snap_combine_kernel<<<(total + 127) / 128, 128, 0, st>>>(NQ, n_parts, inv_c, sc, total);
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return e;
-    if (NQP > 256) {  // two warpgroups accumulate two halves with atomics
-        e = cudaMemsetAsync(sc.colsum, 0, (size_t)d.R * ws.S_pad * 4, st);
-        if (e != cudaSuccess) return e;
-    }
+    e = cudaMemsetAsync(sc.colsum, 0, (size_t)d.R * ws.S_pad * 4, st);  // warpgroups add their halves
+    if (e != cudaSuccess) return e;
     k2<<<grid, kSnThreads, smem, st>>>(mapK, mapQ, d.H, G, d.S, window, d.R, n_tiles128, ctas_per_row, sc,
                                        ws.S_pad);
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return e;
-    dim3 grid3(ws.n_tiles, d.R);
+    dim3 grid3((ws.n_tiles + kFinalizeTiles - 1) / kFinalizeTiles, d.R);
     snap_finalize_kernel<T><<<grid3, kTileThreads, 0, st>>>(d.S, window, kernel_size, 1.0f / (float)NQ, sc, ws,
                                                             static_cast<uint16_t*>(scores_out));
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return e;
