@@ -166,8 +166,8 @@ __device__ __forceinline__ void refine_item(SelectSmem& sm, int row, int group, 
         for (int i = 0; i < 8; ++i) lo[lane * 8 + i] = 0;
         __syncwarp();
         // kTile == 256 keys: one 16-byte load per lane
-        const int4 v = *reinterpret_cast<const int4*>(ws.keys + (size_t)row * ws.S_pad +
-                                                      (size_t)tile * kTile + lane * 8);
+        const int4 v = __ldcg(reinterpret_cast<const int4*>(ws.keys + (size_t)row * ws.S_pad +
+                                                            (size_t)tile * kTile + lane * 8));
         const uint32_t w4[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
         uint32_t n_gt = 0;
 #pragma unroll
@@ -237,7 +237,6 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = row / H, h = row % H;
     const int s = tile * kTile + tid;
-    const uint32_t key = ws.keys[(size_t)row * ws.S_pad + s];  // independent of the refine stage
     // wait until the row scan has published (bounded spin; traps instead of hanging the GPU)
     if (tid == 0) {
         const volatile uint32_t* flag = ws.counters + 1 + ws.R + row;
@@ -249,6 +248,9 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
         __threadfence();
     }
     __syncthreads();
+    // (in the fused Knorm kernel the keys are produced by earlier items of the same launch: read them
+    // only after the flag, through L2)
+    const uint32_t key = __ldcg(&ws.keys[(size_t)row * ws.S_pad + s]);
     const uint2 meta = __ldcg(&ws.row_meta[row]);
     const uint2 before = __ldcg(&ws.tile_prefix[(size_t)row * ws.n_tiles + tile]);
     const uint32_t T = meta.x, n_take = meta.y;
