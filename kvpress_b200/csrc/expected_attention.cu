@@ -19,6 +19,7 @@
 //       fp32, rounds it ONCE to the cache dtype, and emits keys + histogram for the select stage.
 // Covariance-free mode (use_covariance=False) is a plain streaming GEMV kernel.
 #include "common.cuh"
+#include "knorm_chunk.cuh"
 #include "umma.cuh"
 
 namespace kvp {
@@ -33,12 +34,11 @@ __device__ long long g_ea_prof[32];
 #endif
 
 constexpr int kEaTile = 128;      // key rows per MMA tile (M)
-constexpr int kEaThreads = 512;   // 16 warps: TMA, MMA, TMEM-alloc, spare, 2x4 epilogue, 4 V-norm
+constexpr int kEaThreads = 384;   // 12 warps: TMA, MMA, TMEM-alloc, spare, 2 x 4 epilogue
 constexpr int kEaMaxParts = 160;  // upper bound on CTAs per (b,h) row (>= SM count)
 
 struct EaScratch {
     float* logits;    // [R][G][S_pad]
-    float* vnorm;     // [R][S_pad]
     float2* partial;  // [R][G][n_parts] (max, sum exp) per CTA part
 };
 
@@ -49,8 +49,7 @@ size_t ea_scratch_bytes(const Dims& d) {
     const size_t S_pad = (size_t)((d.S + kTile - 1) / kTile) * kTile;
     const size_t n_parts = (size_t)((d.S + kScoreChunkGeneric - 1) / kScoreChunkGeneric);
     const size_t parts = n_parts > kEaMaxParts ? n_parts : kEaMaxParts;
-    return align256((size_t)d.R * G * S_pad * 4) + align256((size_t)d.R * S_pad * 4) +
-           align256((size_t)d.R * G * parts * sizeof(float2));
+    return align256((size_t)d.R * G * S_pad * 4) + align256((size_t)d.R * G * parts * sizeof(float2));
 }
 
 static EaScratch carve_ea(const Dims& d, const Workspace& ws) {
@@ -60,8 +59,6 @@ static EaScratch carve_ea(const Dims& d, const Workspace& ws) {
     EaScratch s;
     s.logits = reinterpret_cast<float*>(p);
     p += align256((size_t)d.R * G * S_pad * 4);
-    s.vnorm = reinterpret_cast<float*>(p);
-    p += align256((size_t)d.R * S_pad * 4);
     s.partial = reinterpret_cast<float2*>(p);
     return s;
 }
@@ -88,9 +85,8 @@ struct EaSmem {
 template <typename T, int D, int G>
 __global__ void __launch_bounds__(kEaThreads, 1)
 ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapCov,
-                 const T* __restrict__ V, Strides3 vs, const T* __restrict__ mu, int H, int Hq, int S,
-                 int n_sink, int use_vnorm, int R, int n_tiles128, int ctas_per_row, int n_parts,
-                 EaScratch sc, int S_pad) {
+                 const T* __restrict__ mu, int H, int Hq, int S, int n_sink, int R, int n_tiles128,
+                 int ctas_per_row, int n_parts, EaScratch sc, int S_pad) {
     using L = EaSmem<D, G>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // dynamic shared memory is only guaranteed 16-B aligned: round up to 1024 B for the swizzle
@@ -349,81 +345,6 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     s_red[((warp - 4) * 2 + q) * 2 + 1] = z;
                 }
             }
-        } else if (warp >= 12 || warp == 2 || warp == 3) {
-            // ===== V norms for the same tiles: software-pipelined streaming loads. Each warp-wide load
-            // covers 2 rows (16 lanes x 16 B per row); a "group" is 8 such loads (16 rows per warp,
-            // 64 rows per 4 warps); the loads of group i+1 are in flight while group i is reduced, and
-            // the 4-level shuffle reductions of the 8 rows of a group run in lockstep (ILP 8). =====
-            if (use_vnorm) {
-                EA_T0();
-                constexpr int NVW = 6;                               // V-norm warps: 2, 3, 12..15
-                const int vw = warp >= 12 ? warp - 10 : warp - 2;
-                const int sub = lane & 15, rsel = lane >> 4;
-                constexpr int nvec = D / 8;
-                constexpr int GRP = 6;                               // loads per lane per group
-                constexpr int ROWS_PER_GRP = GRP * 2 * NVW;          // rows per group over all V warps
-                const T* vbase = V + (int64_t)b * vs.b + (int64_t)h * vs.h + sub * 8;
-                const uint64_t pol = l2_policy_evict_first();
-                const int s_lo = t_begin * kEaTile;
-                const int s_hi = min(S, t_end * kEaTile);
-                const int n_grp = (s_hi - s_lo + ROWS_PER_GRP - 1) / ROWS_PER_GRP;
-                // ring of three register buffers: one being reduced, two in flight
-                int4 buf[3][GRP];
-                auto issue = [&](int4 (&dst)[GRP], int grp) {
-#pragma unroll
-                    for (int u = 0; u < GRP; ++u) {
-                        const int s = s_lo + grp * ROWS_PER_GRP + u * (2 * NVW) + vw * 2 + rsel;
-                        dst[u] = make_int4(0, 0, 0, 0);
-#ifdef KVP_EA_VPLAIN
-                        if (s < s_hi && sub < nvec) dst[u] = ldg_plain(vbase + (int64_t)s * vs.s);
-#else
-                        if (s < s_hi && sub < nvec) dst[u] = ldg_hint(vbase + (int64_t)s * vs.s, pol);
-#endif
-                    }
-                };
-                auto reduce = [&](const int4 (&src)[GRP], int grp) {
-                    float ss[GRP];
-#pragma unroll
-                    for (int u = 0; u < GRP; ++u) {
-                        const uint32_t w4[4] = {(uint32_t)src[u].x, (uint32_t)src[u].y, (uint32_t)src[u].z,
-                                                (uint32_t)src[u].w};
-                        uint64_t a2 = 0ull;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint64_t f2 = pack_f32x2(F16Traits<T>::unpack2(w4[j]));
-                            a2 = fma_f32x2(f2, f2, a2);
-                        }
-                        const float2 a = unpack_f32x2(a2);
-                        ss[u] = a.x + a.y;
-                    }
-#pragma unroll
-                    for (int off = 8; off >= 1; off >>= 1) {
-#pragma unroll
-                        for (int u = 0; u < GRP; ++u) ss[u] += __shfl_xor_sync(0xFFFFFFFFu, ss[u], off);
-                    }
-#pragma unroll
-                    for (int u = 0; u < GRP; ++u) {
-                        const int s = s_lo + grp * ROWS_PER_GRP + u * (2 * NVW) + vw * 2 + rsel;
-                        if (sub == 0 && s < s_hi) sc.vnorm[(size_t)row * S_pad + s] = sqrtf(ss[u]);
-                    }
-                };
-                if (n_grp > 0) issue(buf[0], 0);
-                if (n_grp > 1) issue(buf[1], 1);
-                // unrolled by 3 so the ring indices are compile-time constants (registers, not local memory)
-                for (int grp = 0; grp < n_grp; grp += 3) {
-                    if (grp + 2 < n_grp) issue(buf[2], grp + 2);
-                    reduce(buf[0], grp);
-                    if (grp + 1 < n_grp) {
-                        if (grp + 3 < n_grp) issue(buf[0], grp + 3);
-                        reduce(buf[1], grp + 1);
-                    }
-                    if (grp + 2 < n_grp) {
-                        if (grp + 4 < n_grp) issue(buf[1], grp + 4);
-                        reduce(buf[2], grp + 2);
-                    }
-                }
-                if (warp == 12 && lane == 0) EA_ACC(6);
-            }
         }
         // ---- CTA-level softmax statistics of this (row, part) -> partial[row][g][part] ---------------
         __syncthreads();
@@ -448,80 +369,94 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     if (warp == 2) umma::tmem_dealloc(tmem, 512);
 }
 
-// ---- covariance-free logits: mu.k / sqrt(d) (+ ||v||) with plain streaming loads -------------------
-template <typename T>
+// ---- covariance-free logits: mu.k / sqrt(d) with plain streaming loads (use_covariance=False) -------
+template <typename T, int LPR>
 __global__ void __launch_bounds__(256)
-ea_mu_logits_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks, Strides3 vs,
-                    const T* __restrict__ mu, int H, int Hq, int G, int S, int D, int n_sink,
-                    int use_vnorm, int n_parts, EaScratch sc, int S_pad) {
+ea_mu_logits_kernel(const T* __restrict__ K, Strides3 ks, const T* __restrict__ mu, int H, int Hq, int G,
+                    int S, int D, int n_sink, int n_parts, EaScratch sc, int S_pad) {
     __shared__ float s_mu[8 * 256];
     __shared__ float s_red[8][8][2];
     const int chunk = blockIdx.x, row = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = row / H, h = row % H;
     const int hq0 = b * Hq + h * G;
-    const float scale = rsqrtf((float)D);
+    const float scale = 1.0f / sqrtf((float)D);
     for (int i = tid; i < G * D; i += 256)
         s_mu[i] = F16Traits<T>::to_float(reinterpret_cast<const uint16_t*>(mu)[(size_t)hq0 * D + i]);
     __syncthreads();
-    // 32 lanes cover one row: lane handles 16-byte pieces lane, lane+32 (D <= 256 -> at most 1)
+    constexpr int RPW = 32 / LPR;
+    constexpr int TOK_PER_WARP = kScoreChunkGeneric / 8;
+    constexpr int ITERS = TOK_PER_WARP / RPW;
+    constexpr int U = (ITERS < 4) ? ITERS : 4;
+    const int sub = lane % LPR, rsel = lane / LPR;
     const int nvec = D >> 3;
+    const T* base = K + (int64_t)b * ks.b + (int64_t)h * ks.h + (int64_t)sub * 8;
+    const int s_warp = chunk * kScoreChunkGeneric + warp * TOK_PER_WARP;
     float run_m[8], run_z[8];
+#pragma unroll
     for (int g = 0; g < 8; ++g) {
         run_m[g] = -INFINITY;
         run_z[g] = 0.f;
     }
-    for (int i = 0; i < kScoreChunkGeneric / 8; ++i) {
-        const int s = chunk * kScoreChunkGeneric + warp * (kScoreChunkGeneric / 8) + i;
-        if (s >= S) break;
-        float kf[8];
-        float vv = 0.f;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it += U) {
+        int4 v[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) kf[j] = 0.f;
-        if (lane < nvec) {
-            const int4 kv = ldg_plain(K + (int64_t)b * ks.b + (int64_t)h * ks.h + (int64_t)s * ks.s + lane * 8);
-            const uint32_t w4[4] = {(uint32_t)kv.x, (uint32_t)kv.y, (uint32_t)kv.z, (uint32_t)kv.w};
+        for (int u = 0; u < U; ++u) {
+            const int s = s_warp + (it + u) * RPW + rsel;
+            v[u] = make_int4(0, 0, 0, 0);
+            if (s < S && sub < nvec) v[u] = ldg_plain(base + (int64_t)s * ks.s);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int s = s_warp + (it + u) * RPW + rsel;
+            const uint32_t w4[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z, (uint32_t)v[u].w};
+            float kf[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float2 f = F16Traits<T>::unpack2(w4[j]);
                 kf[2 * j] = f.x;
                 kf[2 * j + 1] = f.y;
             }
-            if (use_vnorm) {
-                const int4 v4 = ldg_plain(V + (int64_t)b * vs.b + (int64_t)h * vs.h + (int64_t)s * vs.s + lane * 8);
-                const uint32_t x4[4] = {(uint32_t)v4.x, (uint32_t)v4.y, (uint32_t)v4.z, (uint32_t)v4.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = F16Traits<T>::unpack2(x4[j]);
-                    vv = fmaf(f.x, f.x, vv);
-                    vv = fmaf(f.y, f.y, vv);
+            for (int g = 0; g < 8; ++g) {
+                if (g < G) {
+                    float dot = 0.f;
+                    if (sub < nvec) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dot = fmaf(kf[j], s_mu[g * D + sub * 8 + j], dot);
+                    }
+#pragma unroll
+                    for (int off = LPR / 2; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xFFFFFFFFu, dot, off);
+                    const float lg = dot * scale;
+                    if (sub == 0 && s >= n_sink && s < S) {
+                        sc.logits[((size_t)row * G + g) * S_pad + s] = lg;
+                        const float mn = fmaxf(run_m[g], lg);
+                        run_z[g] = run_z[g] * __expf(run_m[g] - mn) + __expf(lg - mn);
+                        run_m[g] = mn;
+                    }
                 }
             }
         }
+    }
+    // merge the per-lane statistics (only lanes with sub == 0 hold any)
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) vv += __shfl_xor_sync(0xFFFFFFFFu, vv, off);
-        if (lane == 0 && use_vnorm) sc.vnorm[(size_t)row * S_pad + s] = sqrtf(vv);
-        for (int g = 0; g < G; ++g) {
-            float dot = 0.f;
-            if (lane < nvec) {
+    for (int g = 0; g < 8; ++g) {
+        if (g < G) {
+            float m = run_m[g], z = run_z[g];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dot = fmaf(kf[j], s_mu[g * D + lane * 8 + j], dot);
+            for (int off = 16; off >= 1; off >>= 1) {
+                const float m2 = __shfl_xor_sync(0xFFFFFFFFu, m, off);
+                const float z2 = __shfl_xor_sync(0xFFFFFFFFu, z, off);
+                const float mn = fmaxf(m, m2);
+                z = (mn == -INFINITY) ? 0.f : z * __expf(m - mn) + z2 * __expf(m2 - mn);
+                m = mn;
             }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xFFFFFFFFu, dot, off);
-            const float lg = dot * scale;
-            if (s >= n_sink) {
-                if (lane == 0) sc.logits[((size_t)row * G + g) * S_pad + s] = lg;
-                const float mn = fmaxf(run_m[g], lg);
-                run_z[g] = run_z[g] * __expf(run_m[g] - mn) + __expf(lg - mn);
-                run_m[g] = mn;
+            if (lane == 0) {
+                s_red[warp][g][0] = m;
+                s_red[warp][g][1] = z;
             }
         }
     }
-    if (lane == 0)
-        for (int g = 0; g < G; ++g) {
-            s_red[warp][g][0] = run_m[g];
-            s_red[warp][g][1] = run_z[g];
-        }
     __syncthreads();
     if (tid < G) {
         float m = -INFINITY, z = 0.f;
@@ -536,10 +471,12 @@ ea_mu_logits_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 k
 }
 
 // ---- finalize: softmax normalisation, group mean, * ||v||, ONE rounding, keys + histogram -----------
-template <typename T>
+template <typename T, int LPR>
 __global__ void __launch_bounds__(kTileThreads)
-ea_finalize_kernel(int G, int S, int n_sink, int use_vnorm, float eps, int n_parts, EaScratch sc,
-                   Workspace ws, uint16_t* __restrict__ scores_out) {
+ea_finalize_kernel(const T* __restrict__ V, Strides3 vs, int H, int D, int G, int S, int n_sink,
+                   int use_vnorm, float eps, int n_parts, EaScratch sc, Workspace ws,
+                   uint16_t* __restrict__ scores_out) {
+    __shared__ float s_vnorm[kTile];
     __shared__ uint16_t skeys[kTile];
     __shared__ uint16_t sscores[kTile];
     __shared__ uint32_t shist[256];
@@ -575,6 +512,11 @@ ea_finalize_kernel(int G, int S, int n_sink, int use_vnorm, float eps, int n_par
         if (t >= ws.n_tiles) break;
         const int s = t * kTile + tid;
         uint16_t bits = 0, key = 0;
+        if (use_vnorm) {  // ||v_s|| for the 256 positions of this sub-tile (streaming pass over V)
+            __syncthreads();
+            row_norm_chunk<T, LPR>(V, vs, row / H, row % H, t, S, D, s_vnorm);
+            __syncthreads();
+        }
         if (s < S) {
             if (s < n_sink) {
                 key = kForcedKey;
@@ -583,7 +525,7 @@ ea_finalize_kernel(int G, int S, int n_sink, int use_vnorm, float eps, int n_par
                 for (int g = 0; g < G; ++g)
                     p += __expf(sc.logits[((size_t)row * G + g) * ws.S_pad + s] - s_m[g]) * s_iz[g];
                 p *= (1.0f / (float)G);
-                const float score = use_vnorm ? (p + eps) * sc.vnorm[(size_t)row * ws.S_pad + s] : p;
+                const float score = use_vnorm ? (p + eps) * s_vnorm[tid] : p;
                 bits = F16Traits<T>::from_float(score);
                 key = ordered_key16(bits, F16Traits<T>::kInfBits);
                 fmax_valid = fmaxf(fmax_valid, F16Traits<T>::to_float(bits));
@@ -643,9 +585,9 @@ cudaError_t launch_fill_sentinel(int dtype, void* scores_out, int R, int S, int 
 
 // ---- host launcher -----------------------------------------------------------------------------------
 template <typename T, int D, int G>
-static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* V, const void* mu,
-                                      const void* cov, int n_sink, int use_vnorm, const Workspace& ws,
-                                      const EaScratch& sc, int* n_parts_out, cudaStream_t st) {
+static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* mu, const void* cov,
+                                      int n_sink, const Workspace& ws, const EaScratch& sc,
+                                      int* n_parts_out, cudaStream_t st) {
     using L = EaSmem<D, G>;
     static int sm_count = 0;
     if (sm_count == 0) {
@@ -686,9 +628,8 @@ static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* 
     auto kern = ea_logits_kernel<T, D, G>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, kEaThreads, smem, st>>>(mapK, mapCov, static_cast<const T*>(V), d.vs,
-                                         static_cast<const T*>(mu), d.H, d.Hq, d.S, n_sink, use_vnorm,
-                                         d.R, n_tiles128, ctas_per_row, ctas_per_row, sc, ws.S_pad);
+    kern<<<grid, kEaThreads, smem, st>>>(mapK, mapCov, static_cast<const T*>(mu), d.H, d.Hq, d.S, n_sink, d.R,
+                                         n_tiles128, ctas_per_row, ctas_per_row, sc, ws.S_pad);
     return cudaPeekAtLastError();
 }
 
@@ -698,30 +639,44 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
                                const Workspace& ws, void* scores_out, cudaStream_t st) {
     const int G = d.Hq / d.H;
     if (G > 8) return cudaErrorNotSupported;
+    const int nvec = d.D / 8;
     const EaScratch sc = carve_ea(d, ws);
     int n_parts = 0;
     cudaError_t e = cudaSuccess;
     if (cov != nullptr) {
         // tensor-core path: head_dim 64 or 128, up to 4 query heads per kv head resident in smem
-        if (d.D == 128 && G == 1) e = launch_ea_logits_t<T, 128, 1>(d, K, V, mu, cov, n_sink, use_vnorm, ws, sc, &n_parts, st);
-        else if (d.D == 128 && G == 2) e = launch_ea_logits_t<T, 128, 2>(d, K, V, mu, cov, n_sink, use_vnorm, ws, sc, &n_parts, st);
-        else if (d.D == 128 && G == 4) e = launch_ea_logits_t<T, 128, 4>(d, K, V, mu, cov, n_sink, use_vnorm, ws, sc, &n_parts, st);
-        else if (d.D == 64 && G == 1) e = launch_ea_logits_t<T, 64, 1>(d, K, V, mu, cov, n_sink, use_vnorm, ws, sc, &n_parts, st);
-        else if (d.D == 64 && G == 2) e = launch_ea_logits_t<T, 64, 2>(d, K, V, mu, cov, n_sink, use_vnorm, ws, sc, &n_parts, st);
-        else if (d.D == 64 && G == 4) e = launch_ea_logits_t<T, 64, 4>(d, K, V, mu, cov, n_sink, use_vnorm, ws, sc, &n_parts, st);
+        if (d.D == 128 && G == 1) e = launch_ea_logits_t<T, 128, 1>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
+        else if (d.D == 128 && G == 2) e = launch_ea_logits_t<T, 128, 2>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
+        else if (d.D == 128 && G == 4) e = launch_ea_logits_t<T, 128, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
+        else if (d.D == 64 && G == 1) e = launch_ea_logits_t<T, 64, 1>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
+        else if (d.D == 64 && G == 2) e = launch_ea_logits_t<T, 64, 2>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
+        else if (d.D == 64 && G == 4) e = launch_ea_logits_t<T, 64, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
         else return cudaErrorNotSupported;
     } else {
         n_parts = (d.S + kScoreChunkGeneric - 1) / kScoreChunkGeneric;
         dim3 grid(n_parts, d.R);
-        ea_mu_logits_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(K), static_cast<const T*>(V), d.ks, d.vs,
-                                                     static_cast<const T*>(mu), d.H, d.Hq, G, d.S, d.D, n_sink,
-                                                     use_vnorm, n_parts, sc, ws.S_pad);
+#define KVP_EA_MU(LPR)                                                                                   \
+    ea_mu_logits_kernel<T, LPR><<<grid, 256, 0, st>>>(static_cast<const T*>(K), d.ks,                     \
+                                                      static_cast<const T*>(mu), d.H, d.Hq, G, d.S, d.D, \
+                                                      n_sink, n_parts, sc, ws.S_pad)
+        if (nvec <= 4) KVP_EA_MU(4);
+        else if (nvec <= 8) KVP_EA_MU(8);
+        else if (nvec <= 16) KVP_EA_MU(16);
+        else KVP_EA_MU(32);
+#undef KVP_EA_MU
         e = cudaPeekAtLastError();
     }
     if (e != cudaSuccess) return e;
     dim3 grid2((ws.n_tiles + kFinalizeTiles - 1) / kFinalizeTiles, d.R);
-    ea_finalize_kernel<T><<<grid2, kTileThreads, 0, st>>>(G, d.S, n_sink, use_vnorm, eps, n_parts, sc, ws,
-                                                          static_cast<uint16_t*>(scores_out));
+#define KVP_EA_FIN(LPR)                                                                                    \
+    ea_finalize_kernel<T, LPR><<<grid2, kTileThreads, 0, st>>>(static_cast<const T*>(V), d.vs, d.H, d.D, G, \
+                                                               d.S, n_sink, use_vnorm, eps, n_parts, sc, ws, \
+                                                               static_cast<uint16_t*>(scores_out))
+    if (nvec <= 4) KVP_EA_FIN(4);
+    else if (nvec <= 8) KVP_EA_FIN(8);
+    else if (nvec <= 16) KVP_EA_FIN(16);
+    else KVP_EA_FIN(32);
+#undef KVP_EA_FIN
     e = cudaPeekAtLastError();
     if (e != cudaSuccess) return e;
     if (scores_out != nullptr) e = launch_fill_sentinel(dtype, scores_out, d.R, d.S, 0, n_sink, ws, st);

@@ -63,4 +63,46 @@ __device__ __forceinline__ void knorm_score_chunk(const T* __restrict__ K, Strid
     }
 }
 
+// ||x_s||_2 in fp32 for the 256 positions of `chunk` of one (b, h) row into shared memory (same access
+// pattern as knorm_score_chunk; loads are L2-evict-first: V is read exactly once).
+template <typename T, int LPR>
+__device__ __forceinline__ void row_norm_chunk(const T* __restrict__ X, Strides3 xs, int b, int h, int chunk,
+                                               int S, int D, float* snorm) {
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int RPW = 32 / LPR;
+    constexpr int TOK_PER_WARP = kScoreChunk / (kTileThreads / 32);
+    constexpr int ITERS = TOK_PER_WARP / RPW;
+    constexpr int U = (ITERS < 8) ? ITERS : 8;
+    const int sub = lane % LPR, rsel = lane / LPR;
+    const int nvec = D >> 3;
+    const T* base = X + (int64_t)b * xs.b + (int64_t)h * xs.h + (int64_t)sub * 8;
+    const int s_warp = chunk * kScoreChunk + warp * TOK_PER_WARP;
+    const uint64_t pol = l2_policy_evict_first();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it += U) {
+        int4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int s = s_warp + (it + u) * RPW + rsel;
+            v[u] = make_int4(0, 0, 0, 0);
+            if (s < S && sub < nvec) v[u] = ldg_hint(base + (int64_t)s * xs.s, pol);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t w[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z, (uint32_t)v[u].w};
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = F16Traits<T>::unpack2(w[j]);
+                ss = fmaf(f.x, f.x, ss);
+                ss = fmaf(f.y, f.y, ss);
+            }
+#pragma unroll
+            for (int off = LPR / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
+            if (sub == 0) snorm[warp * TOK_PER_WARP + (it + u) * RPW + rsel] = sqrtf(ss);
+        }
+    }
+}
+
 }  // namespace kvp
