@@ -59,17 +59,18 @@ static WsLayout layout(const Dims& d, int scorer, int window) {
     L.n_tiles = (d.S + kTile - 1) / kTile;
     L.S_pad = L.n_tiles * kTile;
     size_t off = 0;
-    L.hist_off = off;  // hist_hi then hist_lo, zeroed together by one memset node
-    L.hist_bytes = ((size_t)d.R * 256 * 2 + (size_t)d.R * 3 + 64) * sizeof(uint32_t);
-    off = align_up(off + L.hist_bytes, 256);
+    // one zeroed region (a single memset node per call): hist_hi, hist_lo, counters, tile_prefix
+    L.hist_off = off;
+    off = align_up(off + ((size_t)d.R * 256 * 2 + (size_t)d.R * 3 + 64) * sizeof(uint32_t), 256);
+    L.prefix_off = off;
+    off = align_up(off + (size_t)d.R * L.n_tiles * sizeof(uint2), 256);
+    L.hist_bytes = off - L.hist_off;
     L.keys_off = off;
     off = align_up(off + (size_t)d.R * L.S_pad * sizeof(uint16_t), 256);
     L.sfx_off = off;
     off = align_up(off + (size_t)d.R * L.n_tiles * kSfxStride * sizeof(uint16_t), 256);
     L.meta_off = off;
     off = align_up(off + (size_t)d.R * sizeof(uint2), 256);
-    L.prefix_off = off;
-    off = align_up(off + (size_t)d.R * L.n_tiles * sizeof(uint2), 256);
     L.scorer_off = off;
     L.scorer_bytes = 0;
     if (scorer == KVP_SCORER_SNAPKV) L.scorer_bytes = snapkv_scratch_bytes(d, window);

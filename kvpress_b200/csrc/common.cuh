@@ -35,7 +35,8 @@ struct Workspace {
     uint32_t* counters;  // [0] work-queue ticket, [1 + row] refine items done, [1 + R + row] row ready;
                          // zeroed together with the histograms
     uint2* row_meta;     // [R] {threshold key T, ties to take}
-    uint2* tile_prefix;  // [R][n_tiles] {kept (> T), tied (== T)} positions in the tiles before
+    uint2* tile_prefix;  // [R][n_tiles] {kept (> T) + 1, tied (== T) + 1} positions in the tiles before;
+                         // zero = row not scanned yet
     int R;
     void* scorer;        // scorer-specific scratch (SnapKV / ExpectedAttention)
     size_t scorer_bytes;

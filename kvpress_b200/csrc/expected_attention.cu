@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(kTileThreads)
 ea_finalize_kernel(const T* __restrict__ V, Strides3 vs, int H, int D, int G, int S, int n_sink,
                    int use_vnorm, float eps, int n_parts, EaScratch sc, Workspace ws,
                    uint16_t* __restrict__ scores_out) {
-    __shared__ float s_vnorm[kTile];
+    __shared__ float s_vnorm[kFinalizeTiles * kTile];
     __shared__ uint16_t skeys[kTile];
     __shared__ uint16_t sscores[kTile];
     __shared__ uint32_t shist[256];
@@ -506,17 +506,19 @@ ea_finalize_kernel(const T* __restrict__ V, Strides3 vs, int H, int D, int G, in
         }
     }
     __syncthreads();
+    if (use_vnorm) {  // ||v_s|| for this CTA's positions: one streaming pass over V, no barriers inside
+        for (int sub = 0; sub < kFinalizeTiles; ++sub) {
+            const int t = tile * kFinalizeTiles + sub;
+            if (t < ws.n_tiles) row_norm_chunk<T, LPR>(V, vs, row / H, row % H, t, S, D, s_vnorm + sub * kTile);
+        }
+        __syncthreads();
+    }
     float fmax_valid = -INFINITY;
     for (int sub = 0; sub < kFinalizeTiles; ++sub) {
         const int t = tile * kFinalizeTiles + sub;
         if (t >= ws.n_tiles) break;
         const int s = t * kTile + tid;
         uint16_t bits = 0, key = 0;
-        if (use_vnorm) {  // ||v_s|| for the 256 positions of this sub-tile (streaming pass over V)
-            __syncthreads();
-            row_norm_chunk<T, LPR>(V, vs, row / H, row % H, t, S, D, s_vnorm);
-            __syncthreads();
-        }
         if (s < S) {
             if (s < n_sink) {
                 key = kForcedKey;
@@ -525,7 +527,7 @@ ea_finalize_kernel(const T* __restrict__ V, Strides3 vs, int H, int D, int G, in
                 for (int g = 0; g < G; ++g)
                     p += __expf(sc.logits[((size_t)row * G + g) * ws.S_pad + s] - s_m[g]) * s_iz[g];
                 p *= (1.0f / (float)G);
-                const float score = use_vnorm ? (p + eps) * s_vnorm[tid] : p;
+                const float score = use_vnorm ? (p + eps) * s_vnorm[sub * kTile + tid] : p;
                 bits = F16Traits<T>::from_float(score);
                 key = ordered_key16(bits, F16Traits<T>::kInfBits);
                 fmax_valid = fmaxf(fmax_valid, F16Traits<T>::to_float(bits));

@@ -31,7 +31,7 @@ __device__ __forceinline__ void copy_rows_kv(const char* __restrict__ srcK, int6
                                              char* __restrict__ dstK, char* __restrict__ dstV,
                                              int64_t dst_row_bytes, const int* __restrict__ list,
                                              int count, int nvec) {
-    constexpr int U = 4;
+    constexpr int U = 2;
     const int total = count * nvec;
     const uint64_t pol_first = l2_policy_evict_first();
     for (int base = threadIdx.x; base < total; base += kTileThreads * U) {
@@ -92,6 +92,9 @@ __device__ __forceinline__ void scan_row(SelectSmem& sm, int row, int n_kept, co
     }
     __syncthreads();
     const uint32_t lo1 = sm.thr[2];
+    if (tid == 0) ws.row_meta[row] = make_uint2(sm.thr[0], sm.thr[1]);
+    __threadfence();  // row_meta is visible before any prefix (= readiness) is
+    __syncthreads();
     const uint16_t* recs = ws.tile_sfx + (size_t)row * ws.n_tiles * kSfxStride;
     uint2* prefix = ws.tile_prefix + (size_t)row * ws.n_tiles;
     uint32_t carry_gt = 0, carry_eq = 0;
@@ -128,16 +131,15 @@ __device__ __forceinline__ void scan_row(SelectSmem& sm, int row, int n_kept, co
             tg += sm.wsum[0][w];
             te += sm.wsum[1][w];
         }
-        if (t < ws.n_tiles) prefix[t] = make_uint2(pg + igt - gt, pe + ieq - eq);
+        if (t < ws.n_tiles) {
+            const uint2 val = make_uint2(pg + igt - gt + 1u, pe + ieq - eq + 1u);  // +1: 0 means not ready
+            // 8-byte store: both halves become visible together
+            *reinterpret_cast<volatile unsigned long long*>(prefix + t) =
+                (unsigned long long)val.x | ((unsigned long long)val.y << 32);
+        }
         carry_gt += tg;
         carry_eq += te;
     }
-    if (tid == 0) {
-        ws.row_meta[row] = make_uint2(sm.thr[0], sm.thr[1]);
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) atomicExch(&ws.counters[1 + ws.R + row], 1u);
 }
 
 // ---- refine item: (row, group of kGroupTiles tiles); one warp per tile, no block barriers inside ----
@@ -237,22 +239,28 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = row / H, h = row % H;
     const int s = tile * kTile + tid;
-    // wait until the row scan has published (bounded spin; traps instead of hanging the GPU)
+    // The row scan publishes tile_prefix[row][tile] = {kept_before + 1, tied_before + 1} last (the table is
+    // zeroed by the per-call memset), so one polled load doubles as the readiness flag (bounded spin;
+    // traps instead of hanging the GPU).
+    const uint32_t key = __ldcg(&ws.keys[(size_t)row * ws.S_pad + s]);
     if (tid == 0) {
-        const volatile uint32_t* flag = ws.counters + 1 + ws.R + row;
+        const volatile unsigned long long* slot =
+            reinterpret_cast<const volatile unsigned long long*>(ws.tile_prefix + (size_t)row * ws.n_tiles + tile);
         uint32_t spins = 0;
-        while (*flag == 0u) {
+        unsigned long long raw = *slot;
+        while ((uint32_t)raw == 0u || (uint32_t)(raw >> 32) == 0u) {
             __nanosleep(64);
             if (++spins > (1u << 24)) __trap();
+            raw = *slot;
         }
+        const uint2 v = make_uint2((uint32_t)raw, (uint32_t)(raw >> 32));
         __threadfence();
+        sm.thr[0] = v.x - 1u;
+        sm.thr[1] = v.y - 1u;
     }
     __syncthreads();
-    // (in the fused Knorm kernel the keys are produced by earlier items of the same launch: read them
-    // only after the flag, through L2)
-    const uint32_t key = __ldcg(&ws.keys[(size_t)row * ws.S_pad + s]);
     const uint2 meta = __ldcg(&ws.row_meta[row]);
-    const uint2 before = __ldcg(&ws.tile_prefix[(size_t)row * ws.n_tiles + tile]);
+    const uint2 before = make_uint2(sm.thr[0], sm.thr[1]);
     const uint32_t T = meta.x, n_take = meta.y;
     const uint32_t gt_before = before.x, eq_before = before.y;
 
@@ -298,7 +306,7 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
 // flag), items [nA, nA + nB) the compact items (last rows / last tiles first, so K rows the score
 // stage touched last are re-read while still in L2). A compact item only waits for refine items,
 // which precede it in the queue and never wait themselves => no deadlock for any grid size.
-__global__ void __launch_bounds__(kTileThreads, 4)
+__global__ void __launch_bounds__(kTileThreads, 5)
 select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, Strides3 ks,
                       Strides3 vs, char* __restrict__ K_out, char* __restrict__ V_out,
                       int32_t* __restrict__ idx_out, int H, int S, int D, int n_kept,
