@@ -113,6 +113,9 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     static_assert(kN <= 256, "two heads must fit one MMA");
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef KVP_EA_PROFILE
+    const long long t_entry = clock64();
+#endif
 
     // ---- which (row, tile range) this CTA owns; rows are visited round-robin -----------------------
     const int n_groups = gridDim.x / ctas_per_row;  // concurrent rows
@@ -234,12 +237,15 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                 run_m[q] = -INFINITY;
                 run_z[q] = 0.f;
             }
+#ifdef KVP_EA_PROFILE
+            if (blockIdx.x == 0 && warp == 4 && lane == 0) g_ea_prof[9] += clock64() - t_entry;
+#endif
             for (int t = t_begin; t < t_end; ++t, ++k_it) {
                 const int stage = k_it & 1;
                 const unsigned char* krow = s_stage + stage * L::kStageBytes;
                 const int s = t * kEaTile + r;
                 const bool valid = (s >= n_sink) && (s < S);
-                bool waited_k = false;
+                bool waited_k = false, released_k = false;
 #pragma unroll 1
                 for (int half = 0; half < kHalves; ++half, ++h_it) {
                     const int buf = h_it & 1;
@@ -312,7 +318,14 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     // accumulator buffer can be overwritten by the next MMA
                     umma::fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) umma::mbar_arrive(&t_empty[buf]);
+                    // Release both resources BEFORE the global stores below: mbarrier.arrive has release
+                    // semantics and would otherwise wait for those stores to complete (~1k cycles per tile).
+                    // A warpgroup drains at most one half per tile, so it is also done with the K tile.
+                    if (lane == 0) {
+                        umma::mbar_arrive(&t_empty[buf]);
+                        umma::mbar_arrive(&k_empty[stage]);
+                    }
+                    released_k = true;
 #pragma unroll
                     for (int q = 0; q < HPH; ++q) {
                         const int g = half * HPH + q;
@@ -326,7 +339,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     }
                 }
                 __syncwarp();
-                if (lane == 0) umma::mbar_arrive(&k_empty[stage]);  // done with (or skipped) this K tile
+                if (!released_k && lane == 0) umma::mbar_arrive(&k_empty[stage]);  // skipped this K tile
             }
             // ---- warp-level (max, sum-exp) per head slot -> shared ---------------------------------------
 #pragma unroll
@@ -364,6 +377,10 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         }
     }
 
+#ifdef KVP_EA_PROFILE
+    if (blockIdx.x == 0 && tid == 0) g_ea_prof[7] += clock64() - t_entry;
+    if (blockIdx.x == 0 && tid == 128) g_ea_prof[8] += clock64() - t_entry;
+#endif
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 2) umma::tmem_dealloc(tmem, 512);

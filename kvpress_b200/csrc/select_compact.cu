@@ -242,7 +242,6 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
     // The row scan publishes tile_prefix[row][tile] = {kept_before + 1, tied_before + 1} last (the table is
     // zeroed by the per-call memset), so one polled load doubles as the readiness flag (bounded spin;
     // traps instead of hanging the GPU).
-    const uint32_t key = __ldcg(&ws.keys[(size_t)row * ws.S_pad + s]);
     if (tid == 0) {
         const volatile unsigned long long* slot =
             reinterpret_cast<const volatile unsigned long long*>(ws.tile_prefix + (size_t)row * ws.n_tiles + tile);
@@ -259,6 +258,7 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
         sm.thr[1] = v.y - 1u;
     }
     __syncthreads();
+    const uint32_t key = __ldcg(&ws.keys[(size_t)row * ws.S_pad + s]);
     const uint2 meta = __ldcg(&ws.row_meta[row]);
     const uint2 before = make_uint2(sm.thr[0], sm.thr[1]);
     const uint32_t T = meta.x, n_take = meta.y;

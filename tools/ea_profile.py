@@ -18,7 +18,7 @@ bench.run_native(w, K, V, extra, n_kept)
 torch.cuda.synchronize()
 lib.kvp_debug_ea_profile(buf, 0)
 names = ["producer wait k_empty", "mma wait k_full", "mma wait t_empty", "epi(WG0 w4) wait k_full", "epi wait t_full",
-         "epi compute (per half)", "(unused)"]
+         "epi compute (per half)", "(unused)", "thread 0: entry -> exit", "thread 128 (epi): entry -> exit", "epi warp: entry -> first tile"]
 tiles = 57
 for i, n in enumerate(names):
     print(f"{n:28s} {buf[i]:10d} cycles  = {buf[i] / tiles:9.0f} per tile")
