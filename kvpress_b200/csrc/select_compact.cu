@@ -20,42 +20,73 @@
 
 namespace kvp {
 
-constexpr int kTilesPerWarp = 4;                                  // refine: tiles per warp
-constexpr int kGroupTiles = (kTileThreads / 32) * kTilesPerWarp;  // tiles per refine item (32)
+#ifdef KVP_SEL_PROFILE
+__device__ long long g_sel_prof[16];
+#define SEL_T0(name) const long long name = clock64()
+#define SEL_ACC(slot, name) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_sel_prof[slot] += clock64() - name; } while (0)
+#define SEL_CNT(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_sel_prof[slot] += 1; } while (0)
+extern "C" void kvp_debug_sel_profile(long long* out, int reset) {
+    if (reset) {
+        long long z[16] = {0};
+        cudaMemcpyToSymbol(g_sel_prof, z, sizeof(z));
+    } else {
+        cudaMemcpyFromSymbol(out, g_sel_prof, 16 * sizeof(long long));
+    }
+}
+#else
+#define SEL_T0(name) do {} while (0)
+#define SEL_ACC(slot, name) do {} while (0)
+#define SEL_CNT(slot) do {} while (0)
+#endif
+
+constexpr int kTilesPerWarp = 2;                                  // refine: tiles per warp
+constexpr int kGroupTiles = (kTileThreads / 32) * kTilesPerWarp;  // tiles per refine item (16)
 
 // Copies `count` rows of `nvec` 16-byte vectors of BOTH tensors: dst row j <- src row list[j].
 // K rows are plain loads (they may still sit in L2 from the score stage), V rows and all stores are
-// streamed (evict-first). 2*U independent 16-byte loads are in flight per thread.
+// streamed (evict-first). The loads of two consecutive batches (2 x 2*U 16-byte loads per thread) are
+// issued before the first store, so a typical item (<= 128 kept rows of 256 B) is ONE memory round trip.
 __device__ __forceinline__ void copy_rows_kv(const char* __restrict__ srcK, int64_t k_row_bytes,
                                              const char* __restrict__ srcV, int64_t v_row_bytes,
                                              char* __restrict__ dstK, char* __restrict__ dstV,
                                              int64_t dst_row_bytes, const int* __restrict__ list,
                                              int count, int nvec) {
-    constexpr int U = 2;
+    constexpr int U = 4;
+    constexpr int STEP = kTileThreads * U;
     const int total = count * nvec;
     const uint64_t pol_first = l2_policy_evict_first();
-    for (int base = threadIdx.x; base < total; base += kTileThreads * U) {
-        int4 vk[U], vv[U];
-        int64_t doff[U];
+    auto load = [&](int4 (&vk)[U], int4 (&vv)[U], int base) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int i = base + u * kTileThreads;
-            doff[u] = -1;
             if (i < total) {
                 const int r = i / nvec;
                 const int cc = i - r * nvec;
                 const int64_t src_row = list[r];
-                doff[u] = (int64_t)r * dst_row_bytes + cc * 16;
                 vk[u] = ldg_plain(srcK + src_row * k_row_bytes + cc * 16);
                 vv[u] = ldg_hint(srcV + src_row * v_row_bytes + cc * 16, pol_first);
             }
         }
+    };
+    auto store = [&](const int4 (&vk)[U], const int4 (&vv)[U], int base) {
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (doff[u] >= 0) {
-                stg_hint(dstK + doff[u], vk[u], pol_first);
-                stg_hint(dstV + doff[u], vv[u], pol_first);
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * kTileThreads;
+            if (i < total) {
+                const int r = i / nvec;
+                const int64_t off = (int64_t)r * dst_row_bytes + (i - r * nvec) * 16;
+                stg_hint(dstK + off, vk[u], pol_first);
+                stg_hint(dstV + off, vv[u], pol_first);
             }
+        }
+    };
+    for (int base = threadIdx.x; base < total; base += 2 * STEP) {
+        int4 ak[U], av[U], bk[U], bv[U];
+        load(ak, av, base);
+        const bool second = (base + STEP) < total;
+        if (second) load(bk, bv, base + STEP);
+        store(ak, av, base);
+        if (second) store(bk, bv, base + STEP);
     }
 }
 
@@ -146,6 +177,16 @@ __device__ __forceinline__ void scan_row(SelectSmem& sm, int row, int n_kept, co
 __device__ __forceinline__ void refine_item(SelectSmem& sm, int row, int group, int n_groups, int S,
                                             int n_kept, const Workspace& ws) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // this warp's key tiles are requested first: their latency overlaps the histogram read + search
+    int4 kv[kTilesPerWarp];
+#pragma unroll
+    for (int tw = 0; tw < kTilesPerWarp; ++tw) {
+        const int tile = group * kGroupTiles + warp * kTilesPerWarp + tw;
+        kv[tw] = make_int4(0, 0, 0, 0);
+        if (tile < ws.n_tiles)
+            kv[tw] = __ldcg(reinterpret_cast<const int4*>(ws.keys + (size_t)row * ws.S_pad +
+                                                           (size_t)tile * kTile + lane * 8));
+    }
     sm.hist[tid] = __ldcg(&ws.hist_hi[(size_t)row * 256 + tid]);  // written by other CTAs' atomics
     __syncthreads();
     if (warp == 0) {
@@ -160,16 +201,14 @@ __device__ __forceinline__ void refine_item(SelectSmem& sm, int row, int group, 
     uint32_t acc[8];  // group-level low-byte histogram, bins [8*lane, 8*lane+8) of this warp's tiles
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0;
-#pragma unroll 1
+#pragma unroll
     for (int tw = 0; tw < kTilesPerWarp; ++tw) {
         const int tile = group * kGroupTiles + warp * kTilesPerWarp + tw;
         if (tile >= ws.n_tiles) break;
 #pragma unroll
         for (int i = 0; i < 8; ++i) lo[lane * 8 + i] = 0;
         __syncwarp();
-        // kTile == 256 keys: one 16-byte load per lane
-        const int4 v = __ldcg(reinterpret_cast<const int4*>(ws.keys + (size_t)row * ws.S_pad +
-                                                            (size_t)tile * kTile + lane * 8));
+        const int4 v = kv[tw];
         const uint32_t w4[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
         uint32_t n_gt = 0;
 #pragma unroll
@@ -239,6 +278,7 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = row / H, h = row % H;
     const int s = tile * kTile + tid;
+    SEL_T0(t_wait);
     // The row scan publishes tile_prefix[row][tile] = {kept_before + 1, tied_before + 1} last (the table is
     // zeroed by the per-call memset), so one polled load doubles as the readiness flag (bounded spin;
     // traps instead of hanging the GPU).
@@ -258,6 +298,8 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
         sm.thr[1] = v.y - 1u;
     }
     __syncthreads();
+    SEL_ACC(0, t_wait);
+    SEL_T0(t_rank);
     const uint32_t key = __ldcg(&ws.keys[(size_t)row * ws.S_pad + s]);
     const uint2 meta = __ldcg(&ws.row_meta[row]);
     const uint2 before = make_uint2(sm.thr[0], sm.thr[1]);
@@ -290,6 +332,8 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
     if (is_gt || (is_eq && eq_rank < tie_room)) sm.list[gt_rank + min(eq_rank, tie_room)] = s;
     const int count = (int)(tot_gt + min(tot_eq, tie_room));
     __syncthreads();
+    SEL_ACC(1, t_rank);
+    SEL_T0(t_copy);
     if (count > 0) {
         const int64_t out_row0 = (int64_t)row * n_kept + out_base;
         if (idx_out != nullptr && tid < count) idx_out[out_row0 + tid] = sm.list[tid];
@@ -299,6 +343,8 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
                      K_out + out_row0 * row_bytes, V_out + out_row0 * row_bytes, row_bytes, sm.list,
                      count, D >> 3);
     }
+    SEL_ACC(2, t_copy);
+    SEL_CNT(3);
 }
 
 // Persistent select+compact kernel: CTAs pull items from one ticket counter. Items [0, nA) are the
@@ -306,7 +352,7 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
 // flag), items [nA, nA + nB) the compact items (last rows / last tiles first, so K rows the score
 // stage touched last are re-read while still in L2). A compact item only waits for refine items,
 // which precede it in the queue and never wait themselves => no deadlock for any grid size.
-__global__ void __launch_bounds__(kTileThreads, 5)
+__global__ void __launch_bounds__(kTileThreads, 2)
 select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, Strides3 ks,
                       Strides3 vs, char* __restrict__ K_out, char* __restrict__ V_out,
                       int32_t* __restrict__ idx_out, int H, int S, int D, int n_kept,
@@ -315,14 +361,20 @@ select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, St
     const int R = ws.R;
     const int n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
     const int nA = R * n_groups, nB = R * ws.n_tiles;
+    SEL_T0(t_kernel);
     while (true) {
+        SEL_T0(t_ticket);
         __syncthreads();  // previous item's shared state is dead
         if (threadIdx.x == 0) sm.item = (int)atomicAdd(&ws.counters[0], 1u);
         __syncthreads();
+        SEL_ACC(4, t_ticket);
         const int item = sm.item;
         if (item >= nA + nB) break;
         if (item < nA) {
+            SEL_T0(t_ref);
             refine_item(sm, item / n_groups, item % n_groups, n_groups, S, n_kept, ws);
+            SEL_ACC(5, t_ref);
+            SEL_CNT(6);
         } else {
             const int j = item - nA;
             const int row = R - 1 - j / ws.n_tiles;
@@ -330,6 +382,7 @@ select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, St
             compact_item(sm, row, tile, K, V, ks, vs, K_out, V_out, idx_out, H, S, D, n_kept, ws);
         }
     }
+    SEL_ACC(7, t_kernel);
 }
 
 static int persistent_grid(const void* kernel, int threads, int n_items) {
@@ -423,7 +476,7 @@ __device__ __forceinline__ void spin_until(const uint32_t* counter, uint32_t nee
 }
 
 template <typename T, int LPR>
-__global__ void __launch_bounds__(kTileThreads, 3)
+__global__ void __launch_bounds__(kTileThreads, 2)
 knorm_fused_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks, Strides3 vs,
                    char* __restrict__ K_out, char* __restrict__ V_out, int32_t* __restrict__ idx_out,
                    uint16_t* __restrict__ scores_out, int H, int S, int D, int n_kept, Workspace ws) {
