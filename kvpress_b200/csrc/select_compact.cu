@@ -46,12 +46,12 @@ constexpr int kGroupTiles = (kTileThreads / 32) * kTilesPerWarp;  // tiles per r
 // K rows are plain loads (they may still sit in L2 from the score stage), V rows and all stores are
 // streamed (evict-first). The loads of two consecutive batches (2 x 2*U 16-byte loads per thread) are
 // issued before the first store, so a typical item (<= 128 kept rows of 256 B) is ONE memory round trip.
+template <int U>
 __device__ __forceinline__ void copy_rows_kv(const char* __restrict__ srcK, int64_t k_row_bytes,
                                              const char* __restrict__ srcV, int64_t v_row_bytes,
                                              char* __restrict__ dstK, char* __restrict__ dstV,
                                              int64_t dst_row_bytes, const int* __restrict__ list,
                                              int count, int nvec) {
-    constexpr int U = 4;
     constexpr int STEP = kTileThreads * U;
     const int total = count * nvec;
     const uint64_t pol_first = l2_policy_evict_first();
@@ -338,7 +338,7 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
         const int64_t out_row0 = (int64_t)row * n_kept + out_base;
         if (idx_out != nullptr && tid < count) idx_out[out_row0 + tid] = sm.list[tid];
         const int64_t row_bytes = (int64_t)D * 2;
-        copy_rows_kv(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
+        copy_rows_kv<3>(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
                      V + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2, vs.s * 2,
                      K_out + out_row0 * row_bytes, V_out + out_row0 * row_bytes, row_bytes, sm.list,
                      count, D >> 3);
@@ -352,7 +352,7 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
 // flag), items [nA, nA + nB) the compact items (last rows / last tiles first, so K rows the score
 // stage touched last are re-read while still in L2). A compact item only waits for refine items,
 // which precede it in the queue and never wait themselves => no deadlock for any grid size.
-__global__ void __launch_bounds__(kTileThreads, 2)
+__global__ void __launch_bounds__(kTileThreads, 3)
 select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, Strides3 ks,
                       Strides3 vs, char* __restrict__ K_out, char* __restrict__ V_out,
                       int32_t* __restrict__ idx_out, int H, int S, int D, int n_kept,
@@ -476,7 +476,7 @@ __device__ __forceinline__ void spin_until(const uint32_t* counter, uint32_t nee
 }
 
 template <typename T, int LPR>
-__global__ void __launch_bounds__(kTileThreads, 2)
+__global__ void __launch_bounds__(kTileThreads, 3)
 knorm_fused_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks, Strides3 vs,
                    char* __restrict__ K_out, char* __restrict__ V_out, int32_t* __restrict__ idx_out,
                    uint16_t* __restrict__ scores_out, int H, int S, int D, int n_kept, Workspace ws) {
@@ -572,7 +572,7 @@ streaming_compact_kernel(const char* __restrict__ K, const char* __restrict__ V,
     if (idx_out != nullptr)
         for (int j = tid; j < count; j += kTileThreads) idx_out[out_row0 + j] = s_list[j];
     const int64_t row_bytes = (int64_t)D * 2;
-    copy_rows_kv(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
+    copy_rows_kv<4>(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
                  V + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2, vs.s * 2,
                  K_out + out_row0 * row_bytes, V_out + out_row0 * row_bytes, row_bytes, s_list, count,
                  D >> 3);
