@@ -129,7 +129,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
             umma::mbar_init(&k_full[i], 1);
             umma::mbar_init(&k_empty[i], 1 + 8);  // MMA commit + 8 epilogue warps
             umma::mbar_init(&t_full[i], 1);
-            umma::mbar_init(&t_empty[i], HPH == 2 ? 8 : 4);  // warps that drain one buffer
+            umma::mbar_init(&t_empty[i], 4);      // the 4 warps of the warpgroup that drained it
         }
         umma::mbar_init(cov_full, 1);
         umma::mbar_fence_init();
@@ -226,31 +226,30 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
             }
             ++cov_it;
         } else if (warp >= 4 && warp < 12) {
-            // ===== epilogue: two warpgroups, thread = key row. With two heads per accumulator buffer each
-            // warpgroup reduces ONE head (128 TMEM columns) of EVERY buffer, so a buffer is drained in half
-            // the time and handed back to the MMA issuer sooner; with a single head per buffer (G == 1) the
-            // warpgroups alternate buffers. =====
+            // ===== epilogue: two warpgroups, warpgroup wg drains TMEM buffer wg; thread = key row =====
             const int wg = (warp - 4) >> 2;
             const int ew = warp & 3;       // TMEM lane quarter this warp may access
             const int r = ew * 32 + lane;  // row in tile == TMEM lane
             const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
-            float run_m[kHalves], run_z[kHalves];
+            float run_m[HPH], run_z[HPH];
 #pragma unroll
-            for (int i = 0; i < kHalves; ++i) {
-                run_m[i] = -INFINITY;
-                run_z[i] = 0.f;
+            for (int q = 0; q < HPH; ++q) {
+                run_m[q] = -INFINITY;
+                run_z[q] = 0.f;
             }
+#ifdef KVP_EA_PROFILE
+            if (blockIdx.x == 0 && warp == 4 && lane == 0) g_ea_prof[9] += clock64() - t_entry;
+#endif
             for (int t = t_begin; t < t_end; ++t, ++k_it) {
                 const int stage = k_it & 1;
                 const unsigned char* krow = s_stage + stage * L::kStageBytes;
                 const int s = t * kEaTile + r;
                 const bool valid = (s >= n_sink) && (s < S);
-                bool waited_k = false;
-#pragma unroll
+                bool waited_k = false, released_k = false;
+#pragma unroll 1
                 for (int half = 0; half < kHalves; ++half, ++h_it) {
                     const int buf = h_it & 1;
-                    if (HPH == 1 && buf != wg) continue;
-                    const int q = (HPH == 2) ? wg : 0;  // head of this half this warpgroup reduces
+                    if (buf != wg) continue;
                     if (!waited_k) {
                         EA_T0();
                         umma::mbar_wait(&k_full[stage], (k_it >> 1) & 1);
@@ -264,10 +263,14 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     }
                     EA_T0();
                     umma::fence_after_sync();
-                    const uint32_t tbase = tmem + lane_base + buf * kBufCols + q * D;
-                    uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};  // 4 independent fp32x2 accumulators
-                    // software pipeline over 16-column chunks: the TMEM load of chunk c+1 is in flight
-                    // while chunk c is being reduced
+                    const uint32_t tbase = tmem + lane_base + buf * kBufCols;
+                    uint64_t acc2[HPH][4];  // 4 independent fp32x2 accumulators per head
+#pragma unroll
+                    for (int q = 0; q < HPH; ++q)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc2[q][j] = 0ull;
+                    // software pipeline over steps (16-column chunk c, head q): the TMEM load of step i+1
+                    // is in flight while step i is being reduced
                     constexpr int kC16 = D / 16;
                     uint32_t y[2][16];
                     umma::tmem_ld16(tbase, y[0]);
@@ -289,36 +292,59 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                                 k2[ch * 4 + 3] = pack_f32x2(F16Traits<T>::unpack2(v.w));
                             }
                         }
-                        umma::tmem_ld_wait();
-                        if (c + 1 < kC16) umma::tmem_ld16(tbase + (c + 1) * 16, y[(c + 1) & 1]);
-                        const uint32_t* yy = y[c & 1];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            acc2[j & 3] = fma_f32x2(k2[j], pack_u32x2(yy[2 * j], yy[2 * j + 1]), acc2[j & 3]);
+                        for (int q = 0; q < HPH; ++q) {
+                            constexpr int kSteps = kC16 * HPH;
+                            const int step = c * HPH + q;
+                            umma::tmem_ld_wait();
+                            if (step + 1 < kSteps) {
+                                const int cn = (step + 1) / HPH, qn = (step + 1) % HPH;
+                                umma::tmem_ld16(tbase + qn * D + cn * 16, y[(step + 1) & 1]);
+                            }
+                            const uint32_t* yy = y[step & 1];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                acc2[q][j & 3] = fma_f32x2(k2[j], pack_u32x2(yy[2 * j], yy[2 * j + 1]), acc2[q][j & 3]);
+                        }
                     }
-                    const float2 a0 = unpack_f32x2(acc2[0]), a1 = unpack_f32x2(acc2[1]);
-                    const float2 a2 = unpack_f32x2(acc2[2]), a3 = unpack_f32x2(acc2[3]);
-                    const float lg = (((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y))) * inv_2d;
+                    float acc[HPH];
+#pragma unroll
+                    for (int q = 0; q < HPH; ++q) {
+                        const float2 a0 = unpack_f32x2(acc2[q][0]), a1 = unpack_f32x2(acc2[q][1]);
+                        const float2 a2 = unpack_f32x2(acc2[q][2]), a3 = unpack_f32x2(acc2[q][3]);
+                        acc[q] = ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+                    }
                     if (warp == 4 && lane == 0) EA_ACC(5);
                     // accumulator buffer can be overwritten by the next MMA
                     umma::fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) umma::mbar_arrive(&t_empty[buf]);
-                    const int g = half * HPH + q;
-                    if (valid && g < G) {
-                        sc.logits[((size_t)row * G + g) * S_pad + s] = lg;
-                        const float m_new = fmaxf(run_m[half], lg);
-                        run_z[half] = run_z[half] * __expf(run_m[half] - m_new) + __expf(lg - m_new);
-                        run_m[half] = m_new;
+                    // Release both resources BEFORE the global stores below: mbarrier.arrive has release
+                    // semantics and would otherwise wait for those stores to complete (~1k cycles per tile).
+                    // A warpgroup drains at most one half per tile, so it is also done with the K tile.
+                    if (lane == 0) {
+                        umma::mbar_arrive(&t_empty[buf]);
+                        umma::mbar_arrive(&k_empty[stage]);
+                    }
+                    released_k = true;
+#pragma unroll
+                    for (int q = 0; q < HPH; ++q) {
+                        const int g = half * HPH + q;
+                        const float lg = acc[q] * inv_2d;
+                        if (valid && g < G) {
+                            sc.logits[((size_t)row * G + g) * S_pad + s] = lg;
+                            const float m_new = fmaxf(run_m[q], lg);
+                            run_z[q] = run_z[q] * __expf(run_m[q] - m_new) + __expf(lg - m_new);
+                            run_m[q] = m_new;
+                        }
                     }
                 }
                 __syncwarp();
-                if (lane == 0) umma::mbar_arrive(&k_empty[stage]);  // done with (or skipped) this K tile
+                if (!released_k && lane == 0) umma::mbar_arrive(&k_empty[stage]);  // skipped this K tile
             }
-            // ---- warp-level (max, sum-exp) per half slot -> shared ------------------------------------------
+            // ---- warp-level (max, sum-exp) per head slot -> shared ---------------------------------------
 #pragma unroll
-            for (int hs = 0; hs < kHalves; ++hs) {
-                float m = run_m[hs], z = run_z[hs];
+            for (int q = 0; q < HPH; ++q) {
+                float m = run_m[q], z = run_z[q];
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) {
                     const float m2 = __shfl_xor_sync(0xFFFFFFFFu, m, off);
@@ -328,21 +354,21 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     m = mn;
                 }
                 if (lane == 0) {
-                    s_red[((warp - 4) * 2 + hs) * 2] = m;
-                    s_red[((warp - 4) * 2 + hs) * 2 + 1] = z;
+                    s_red[((warp - 4) * 2 + q) * 2] = m;
+                    s_red[((warp - 4) * 2 + q) * 2 + 1] = z;
                 }
             }
         }
         // ---- CTA-level softmax statistics of this (row, part) -> partial[row][g][part] ---------------
         __syncthreads();
         if (tid < G) {
-            // head g = half * HPH + q was accumulated in slot `half` of the warps of warpgroup q (two heads
-            // per buffer) or of both warpgroups (one head per buffer, alternating tiles)
-            const int g = tid, hs = g / HPH;
+            // head g was accumulated in slot q of the warps of: both warpgroups (one half per tile,
+            // tiles alternate) or warpgroup g / HPH (two halves per tile)
+            const int g = tid, q = g % HPH;
             float m = -INFINITY, z = 0.f;
             for (int w = 0; w < 8; ++w) {
-                if (HPH == 2 && (w >> 2) != (g % HPH)) continue;
-                const float m2 = s_red[(w * 2 + hs) * 2], z2 = s_red[(w * 2 + hs) * 2 + 1];
+                if (kHalves == 2 && (w >> 2) != g / HPH) continue;
+                const float m2 = s_red[(w * 2 + q) * 2], z2 = s_red[(w * 2 + q) * 2 + 1];
                 const float mn = fmaxf(m, m2);
                 z = (mn == -INFINITY) ? 0.f : z * __expf(m - mn) + z2 * __expf(m2 - mn);
                 m = mn;

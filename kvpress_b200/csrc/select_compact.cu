@@ -39,6 +39,13 @@ extern "C" void kvp_debug_sel_profile(long long* out, int reset) {
 #define SEL_CNT(slot) do {} while (0)
 #endif
 
+// tuning knobs of the compact items (A/B-tested on the B200, see profiles/)
+#ifndef KVP_SEL_U
+#define KVP_SEL_U 3
+#define KVP_SEL_TWO true
+#define KVP_SEL_CTAS 3
+#endif
+
 constexpr int kTilesPerWarp = 2;                                  // refine: tiles per warp
 constexpr int kGroupTiles = (kTileThreads / 32) * kTilesPerWarp;  // tiles per refine item (16)
 
@@ -46,7 +53,7 @@ constexpr int kGroupTiles = (kTileThreads / 32) * kTilesPerWarp;  // tiles per r
 // K rows are plain loads (they may still sit in L2 from the score stage), V rows and all stores are
 // streamed (evict-first). The loads of two consecutive batches (2 x 2*U 16-byte loads per thread) are
 // issued before the first store, so a typical item (<= 128 kept rows of 256 B) is ONE memory round trip.
-template <int U>
+template <int U, bool kTwoBatches>
 __device__ __forceinline__ void copy_rows_kv(const char* __restrict__ srcK, int64_t k_row_bytes,
                                              const char* __restrict__ srcV, int64_t v_row_bytes,
                                              char* __restrict__ dstK, char* __restrict__ dstV,
@@ -80,13 +87,21 @@ __device__ __forceinline__ void copy_rows_kv(const char* __restrict__ srcK, int6
             }
         }
     };
-    for (int base = threadIdx.x; base < total; base += 2 * STEP) {
-        int4 ak[U], av[U], bk[U], bv[U];
-        load(ak, av, base);
-        const bool second = (base + STEP) < total;
-        if (second) load(bk, bv, base + STEP);
-        store(ak, av, base);
-        if (second) store(bk, bv, base + STEP);
+    if (kTwoBatches) {
+        for (int base = threadIdx.x; base < total; base += 2 * STEP) {
+            int4 ak[U], av[U], bk[U], bv[U];
+            load(ak, av, base);
+            const bool second = (base + STEP) < total;
+            if (second) load(bk, bv, base + STEP);
+            store(ak, av, base);
+            if (second) store(bk, bv, base + STEP);
+        }
+    } else {
+        for (int base = threadIdx.x; base < total; base += STEP) {
+            int4 ak[U], av[U];
+            load(ak, av, base);
+            store(ak, av, base);
+        }
     }
 }
 
@@ -338,7 +353,7 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
         const int64_t out_row0 = (int64_t)row * n_kept + out_base;
         if (idx_out != nullptr && tid < count) idx_out[out_row0 + tid] = sm.list[tid];
         const int64_t row_bytes = (int64_t)D * 2;
-        copy_rows_kv<3>(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
+        copy_rows_kv<KVP_SEL_U, KVP_SEL_TWO>(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
                      V + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2, vs.s * 2,
                      K_out + out_row0 * row_bytes, V_out + out_row0 * row_bytes, row_bytes, sm.list,
                      count, D >> 3);
@@ -352,7 +367,7 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
 // flag), items [nA, nA + nB) the compact items (last rows / last tiles first, so K rows the score
 // stage touched last are re-read while still in L2). A compact item only waits for refine items,
 // which precede it in the queue and never wait themselves => no deadlock for any grid size.
-__global__ void __launch_bounds__(kTileThreads, 3)
+__global__ void __launch_bounds__(kTileThreads, KVP_SEL_CTAS)
 select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, Strides3 ks,
                       Strides3 vs, char* __restrict__ K_out, char* __restrict__ V_out,
                       int32_t* __restrict__ idx_out, int H, int S, int D, int n_kept,
@@ -572,7 +587,7 @@ streaming_compact_kernel(const char* __restrict__ K, const char* __restrict__ V,
     if (idx_out != nullptr)
         for (int j = tid; j < count; j += kTileThreads) idx_out[out_row0 + j] = s_list[j];
     const int64_t row_bytes = (int64_t)D * 2;
-    copy_rows_kv<4>(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
+    copy_rows_kv<4, true>(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
                  V + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2, vs.s * 2,
                  K_out + out_row0 * row_bytes, V_out + out_row0 * row_bytes, row_bytes, s_list, count,
                  D >> 3);

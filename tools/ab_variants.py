@@ -1,0 +1,35 @@
+"""A/B timing of library variants on the same box: each variant runs in a subprocess (its own .so),
+bench-style back-to-back steps with CUDA events; reports us/step for ea_128k and knorm_128k."""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD = r'''
+import os, sys, torch
+sys.path.insert(0, %r)
+from kvpress_b200 import native
+import bench
+native.load()
+out = []
+for wl in ("ea_128k", "knorm_128k"):
+    w = bench.WORKLOADS[wl]
+    K, V, extra = bench.make_inputs(w, "cuda:0", 1)
+    n_kept = bench.kept_count(w["S"], w["ratio"])
+    for _ in range(5): bench.run_native(w, K, V, extra, n_kept)
+    torch.cuda.synchronize()
+    best = 1e9
+    for rep in range(3):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(40): bench.run_native(w, K, V, extra, n_kept)
+        e.record(); torch.cuda.synchronize()
+        best = min(best, s.elapsed_time(e) / 40 * 1e3)
+    out.append("%%s %%.1f" %% (wl, best))
+print("  ".join(out))
+''' % ROOT
+libs = ["default"] + sorted(f for f in os.listdir(os.path.join(ROOT, "tools", "bin")) if f.startswith("libv_"))
+for rnd in range(2):
+    for lib in libs:
+        env = dict(os.environ)
+        if lib != "default":
+            env["KVPRESS_B200_LIB"] = os.path.join(ROOT, "tools", "bin", lib)
+        r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
+        print(f"{lib:22s} {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)
