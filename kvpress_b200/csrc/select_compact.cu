@@ -46,7 +46,6 @@ extern "C" void kvp_debug_sel_profile(long long* out, int reset) {
 #define KVP_SEL_CTAS 3
 #endif
 
-constexpr int kCompactTiles = 4;                                  // tiles per compact item
 constexpr int kTilesPerWarp = 2;                                  // refine: tiles per warp
 constexpr int kGroupTiles = (kTileThreads / 32) * kTilesPerWarp;  // tiles per refine item (16)
 
@@ -109,9 +108,7 @@ __device__ __forceinline__ void copy_rows_kv(const char* __restrict__ srcK, int6
 struct SelectSmem {
     uint32_t hist[256];                    // hist_hi of the current row
     uint32_t lo[kTileThreads / 32][256];   // refine: per-warp low-byte histograms; scan: lo[0] = hist_lo
-    int list[kCompactTiles * kTile];
-    uint32_t before[kCompactTiles][2];
-    uint32_t wsum4[kCompactTiles][2][8];
+    int list[kTile];
     uint32_t wsum[2][8];
     uint32_t thr[3];
     int item;
@@ -288,25 +285,21 @@ __device__ __forceinline__ void refine_item(SelectSmem& sm, int row, int group, 
     }
 }
 
-// ---- compact item: (row, kCompactTiles consecutive tiles); thread tid owns position tid of each tile -------
-// The per-item fixed costs (ticket, readiness poll, metadata loads, barriers) are paid once per 1024
-// positions, and all of the item's kept rows (up to 1024) are copied by one call, i.e. with many
-// independent loads in flight.
-__device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int cgroup, const char* K,
+// ---- compact item: (row, tile of kTile == kTileThreads positions, one per thread) ---------------------
+__device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, const char* K,
                                              const char* V, Strides3 ks, Strides3 vs, char* K_out,
                                              char* V_out, int32_t* idx_out, int H, int S, int D,
                                              int n_kept, const Workspace& ws) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = row / H, h = row % H;
-    const int t0 = cgroup * kCompactTiles;
-    const int nt = min(kCompactTiles, ws.n_tiles - t0);
+    const int s = tile * kTile + tid;
     SEL_T0(t_wait);
     // The row scan publishes tile_prefix[row][tile] = {kept_before + 1, tied_before + 1} last (the table is
     // zeroed by the per-call memset), so one polled load doubles as the readiness flag (bounded spin;
-    // traps instead of hanging the GPU). Thread j polls tile t0 + j.
-    if (tid < nt) {
-        const volatile unsigned long long* slot = reinterpret_cast<const volatile unsigned long long*>(
-            ws.tile_prefix + (size_t)row * ws.n_tiles + t0 + tid);
+    // traps instead of hanging the GPU).
+    if (tid == 0) {
+        const volatile unsigned long long* slot =
+            reinterpret_cast<const volatile unsigned long long*>(ws.tile_prefix + (size_t)row * ws.n_tiles + tile);
         uint32_t spins = 0;
         unsigned long long raw = *slot;
         while ((uint32_t)raw == 0u || (uint32_t)(raw >> 32) == 0u) {
@@ -314,66 +307,51 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int cgroup
             if (++spins > (1u << 24)) __trap();
             raw = *slot;
         }
+        const uint2 v = make_uint2((uint32_t)raw, (uint32_t)(raw >> 32));
         __threadfence();
-        sm.before[tid][0] = (uint32_t)raw - 1u;
-        sm.before[tid][1] = (uint32_t)(raw >> 32) - 1u;
+        sm.thr[0] = v.x - 1u;
+        sm.thr[1] = v.y - 1u;
     }
     __syncthreads();
     SEL_ACC(0, t_wait);
     SEL_T0(t_rank);
-    // (in the fused Knorm kernel the keys are produced by earlier items of the same launch: read them
-    // only after the flag, through L2)
-    uint32_t key[kCompactTiles];
-#pragma unroll
-    for (int j = 0; j < kCompactTiles; ++j)
-        key[j] = (j < nt) ? (uint32_t)__ldcg(&ws.keys[(size_t)row * ws.S_pad + (size_t)(t0 + j) * kTile + tid]) : 0u;
+    const uint32_t key = __ldcg(&ws.keys[(size_t)row * ws.S_pad + s]);
     const uint2 meta = __ldcg(&ws.row_meta[row]);
+    const uint2 before = make_uint2(sm.thr[0], sm.thr[1]);
     const uint32_t T = meta.x, n_take = meta.y;
+    const uint32_t gt_before = before.x, eq_before = before.y;
 
-    unsigned m_gt[kCompactTiles], m_eq[kCompactTiles];
-#pragma unroll
-    for (int j = 0; j < kCompactTiles; ++j) {
-        const bool valid = (j < nt) && ((t0 + j) * kTile + tid) < S;
-        m_gt[j] = __ballot_sync(0xFFFFFFFFu, valid && key[j] > T);
-        m_eq[j] = __ballot_sync(0xFFFFFFFFu, valid && key[j] == T);
-        if (lane == 0) {
-            sm.wsum4[j][0][warp] = __popc(m_gt[j]);
-            sm.wsum4[j][1][warp] = __popc(m_eq[j]);
-        }
+    const bool valid = s < S;
+    const bool is_gt = valid && key > T;
+    const bool is_eq = valid && key == T;
+    const unsigned m_gt = __ballot_sync(0xFFFFFFFFu, is_gt);
+    const unsigned m_eq = __ballot_sync(0xFFFFFFFFu, is_eq);
+    if (lane == 0) {
+        sm.wsum[0][warp] = __popc(m_gt);
+        sm.wsum[1][warp] = __popc(m_eq);
     }
     __syncthreads();
-    const uint32_t out_base = sm.before[0][0] + min(sm.before[0][1], n_take);
-    uint32_t list_base = 0;  // kept rows of the item's earlier tiles
-    const unsigned lt = (1u << lane) - 1u;
+    uint32_t gt_rank = __popc(m_gt & ((1u << lane) - 1u));
+    uint32_t eq_rank = __popc(m_eq & ((1u << lane) - 1u));
+    uint32_t tot_gt = 0, tot_eq = 0;
 #pragma unroll
-    for (int j = 0; j < kCompactTiles; ++j) {
-        if (j < nt) {
-            uint32_t gt_rank = __popc(m_gt[j] & lt), eq_rank = __popc(m_eq[j] & lt);
-            uint32_t tot_gt = 0, tot_eq = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                gt_rank += (w < warp) ? sm.wsum4[j][0][w] : 0u;
-                eq_rank += (w < warp) ? sm.wsum4[j][1][w] : 0u;
-                tot_gt += sm.wsum4[j][0][w];
-                tot_eq += sm.wsum4[j][1][w];
-            }
-            // ties are taken in position order: this tile may take those with global tie rank < n_take
-            const uint32_t eq_before = sm.before[j][1];
-            const uint32_t tie_room = (n_take > eq_before) ? (n_take - eq_before) : 0u;
-            const bool is_gt = (m_gt[j] >> lane) & 1u, is_eq = (m_eq[j] >> lane) & 1u;
-            if (is_gt || (is_eq && eq_rank < tie_room))
-                sm.list[list_base + gt_rank + min(eq_rank, tie_room)] = (t0 + j) * kTile + tid;
-            list_base += tot_gt + min(tot_eq, tie_room);
-        }
+    for (int w = 0; w < 8; ++w) {
+        gt_rank += (w < warp) ? sm.wsum[0][w] : 0u;
+        eq_rank += (w < warp) ? sm.wsum[1][w] : 0u;
+        tot_gt += sm.wsum[0][w];
+        tot_eq += sm.wsum[1][w];
     }
-    const int count = (int)list_base;
+    // ties are taken in position order: this tile may take those with global tie rank < n_take
+    const uint32_t tie_room = (n_take > eq_before) ? (n_take - eq_before) : 0u;
+    const uint32_t out_base = gt_before + min(eq_before, n_take);
+    if (is_gt || (is_eq && eq_rank < tie_room)) sm.list[gt_rank + min(eq_rank, tie_room)] = s;
+    const int count = (int)(tot_gt + min(tot_eq, tie_room));
     __syncthreads();
     SEL_ACC(1, t_rank);
     SEL_T0(t_copy);
     if (count > 0) {
         const int64_t out_row0 = (int64_t)row * n_kept + out_base;
-        if (idx_out != nullptr)
-            for (int j = tid; j < count; j += kTileThreads) idx_out[out_row0 + j] = sm.list[j];
+        if (idx_out != nullptr && tid < count) idx_out[out_row0 + tid] = sm.list[tid];
         const int64_t row_bytes = (int64_t)D * 2;
         copy_rows_kv<KVP_SEL_U, KVP_SEL_TWO>(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
                      V + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2, vs.s * 2,
@@ -397,8 +375,7 @@ select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, St
     __shared__ SelectSmem sm;
     const int R = ws.R;
     const int n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
-    const int n_cgroups = (ws.n_tiles + kCompactTiles - 1) / kCompactTiles;
-    const int nA = R * n_groups, nB = R * n_cgroups;
+    const int nA = R * n_groups, nB = R * ws.n_tiles;
     SEL_T0(t_kernel);
     while (true) {
         SEL_T0(t_ticket);
@@ -415,9 +392,9 @@ select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, St
             SEL_CNT(6);
         } else {
             const int j = item - nA;
-            const int row = R - 1 - j / n_cgroups;
-            const int cgroup = n_cgroups - 1 - j % n_cgroups;
-            compact_item(sm, row, cgroup, K, V, ks, vs, K_out, V_out, idx_out, H, S, D, n_kept, ws);
+            const int row = R - 1 - j / ws.n_tiles;
+            const int tile = ws.n_tiles - 1 - j % ws.n_tiles;
+            compact_item(sm, row, tile, K, V, ks, vs, K_out, V_out, idx_out, H, S, D, n_kept, ws);
         }
     }
     SEL_ACC(7, t_kernel);
@@ -442,7 +419,7 @@ cudaError_t launch_select_compact(const Dims& d, const void* K, const void* V, v
                                   void* V_out, int32_t* idx_out, const Workspace& ws,
                                   cudaStream_t st) {
     const int n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
-    const int n_items = d.R * n_groups + d.R * ((ws.n_tiles + kCompactTiles - 1) / kCompactTiles);
+    const int n_items = d.R * n_groups + d.R * ws.n_tiles;
     const int grid =
         persistent_grid(reinterpret_cast<const void*>(select_compact_kernel), kTileThreads, n_items);
     select_compact_kernel<<<grid, kTileThreads, 0, st>>>(
@@ -455,7 +432,7 @@ cudaError_t launch_select_compact(const Dims& d, const void* K, const void* V, v
 // Work items of three kinds share one ticket queue: S(row, chunk) scores 256 positions and adds to the
 // row histogram; A(row, group) is the refine item (waits until all S items of its row are done);
 // B(row, tile) is the compact item (waits for the row's ready flag). The queue is laid out in blocks
-//     block p = [ A(p-1) | S(p,*) | B(p-2,*) ]
+//     block p = [ A(p-1) | S(p,0) B(p-2,0) S(p,1) B(p-2,1) ... ]
 // so that while row p is being scored (pure HBM reads), row p-2 is compacted: its K rows were read two
 // blocks ago (~2 x 32 MiB of traffic at 128k) and are re-read from the 126 MB L2 instead of HBM, its V
 // reads and all stores are L2-evict-first. Every item only waits on items that precede it in the
@@ -465,12 +442,12 @@ struct FusedItem {
     int row, idx;
 };
 
-__device__ __forceinline__ FusedItem decode_fused_item(long long item, int R, int nT, int nA, int nC) {
+__device__ __forceinline__ FusedItem decode_fused_item(long long item, int R, int nT, int nA) {
     FusedItem it = {-1, 0, 0};
     for (int p = 0; p <= R + 1; ++p) {
         // closed form over the identical middle blocks
         if (p == 2 && R > 2) {
-            const long long full = (long long)nA + nT + nC;
+            const long long full = (long long)nA + 2ll * nT;
             const long long skip = item / full;
             const long long n_mid = R - 2;
             const long long take = skip < n_mid ? skip : n_mid;
@@ -479,7 +456,7 @@ __device__ __forceinline__ FusedItem decode_fused_item(long long item, int R, in
         }
         const int a = (p >= 1 && p <= R) ? nA : 0;
         const int s = (p < R) ? nT : 0;
-        const int b = (p >= 2) ? nC : 0;
+        const int b = (p >= 2) ? nT : 0;
         const long long size = (long long)a + s + b;
         if (item >= size) {
             item -= size;
@@ -487,10 +464,16 @@ __device__ __forceinline__ FusedItem decode_fused_item(long long item, int R, in
         }
         if (item < a) {
             it.kind = 1; it.row = p - 1; it.idx = (int)item;
-        } else if (item < a + s) {
-            it.kind = 0; it.row = p; it.idx = (int)(item - a);
+            return it;
+        }
+        const int j = (int)(item - a);
+        if (s && b) {
+            if (j & 1) { it.kind = 2; it.row = p - 2; it.idx = j >> 1; }
+            else       { it.kind = 0; it.row = p;     it.idx = j >> 1; }
+        } else if (s) {
+            it.kind = 0; it.row = p; it.idx = j;
         } else {
-            it.kind = 2; it.row = p - 2; it.idx = (int)(item - a - s);
+            it.kind = 2; it.row = p - 2; it.idx = j;
         }
         return it;
     }
@@ -515,8 +498,7 @@ knorm_fused_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks
     __shared__ SelectSmem sm;
     const int R = ws.R, nT = ws.n_tiles;
     const int nA = (nT + kGroupTiles - 1) / kGroupTiles;
-    const int nC = (nT + kCompactTiles - 1) / kCompactTiles;
-    const long long total = (long long)R * ((long long)nT + nA + nC);
+    const long long total = (long long)R * (2ll * nT + nA);
     uint32_t* score_done = ws.counters + kCounterMaxSlot(R) + 1;  // [R]
     uint16_t* skeys = reinterpret_cast<uint16_t*>(sm.list);       // 2 x 256 u16 alias the 1 KB list
     uint16_t* sscores = skeys + kScoreChunk;
@@ -527,7 +509,7 @@ knorm_fused_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks
         __syncthreads();
         const long long item = (long long)(uint32_t)sm.item;
         if (item >= total) break;
-        const FusedItem it = decode_fused_item(item, R, nT, nA, nC);
+        const FusedItem it = decode_fused_item(item, R, nT, nA);
         if (it.kind == 0) {
             sm.hist[tid] = 0;
             knorm_score_chunk<T, LPR>(K, ks, it.row / H, it.row % H, it.idx, S, D, skeys, sscores);
@@ -553,8 +535,7 @@ static cudaError_t launch_knorm_fused_t(const Dims& d, const void* K, const void
                                         void* V_out, int32_t* idx_out, void* scores_out,
                                         const Workspace& ws, cudaStream_t st) {
     const int nA = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
-    const int nC = (ws.n_tiles + kCompactTiles - 1) / kCompactTiles;
-    const long long total = (long long)d.R * ((long long)ws.n_tiles + nA + nC);
+    const long long total = (long long)d.R * (2ll * ws.n_tiles + nA);
     if (total > 0x7FFFFFFFll) return cudaErrorNotSupported;
     const int nvec = d.D / 8;
 #define KVP_LAUNCH_FUSED(LPR)                                                                         \
