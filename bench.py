@@ -69,12 +69,32 @@ def algorithmic_bytes(w: dict, n_kept: int) -> int:
     return per_head * w["B"] * w["Hkv"]
 
 
+def algorithmic_flops(w: dict) -> float:
+    """dense FLOPs of the tensor-core score stage (0 for the streaming scorers)."""
+    B, Hq, S, D = w["B"], w["Hq"], w["S"], w["D"]
+    if w["scorer"] == "expected_attention":
+        return float(B * Hq * S * (2 * D * D + 4 * D))
+    if w["scorer"] == "snapkv":
+        return float(2 * 2 * 64 * B * Hq * S * D)  # two exact-softmax passes of 2*w*Hq*S*D
+    return 0.0
+
+
+def load_traffic(workload: str):
+    """DRAM bytes one compress call moves (sum over its kernels, dram__bytes_read + write per launch) from the
+    committed ncu launch list of the same command: profiles/traffic.json, written by tools/ncu_launches.py."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        return json.loads(p.read_text()).get(workload)
+    return None
+
+
 def load_peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
-    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops", 1590.0)),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -347,6 +367,16 @@ def main():
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
         "peak_source": peaks["source"], "algorithmic_bytes_per_launch": abytes, "traffic": None,
     }
+    tr = load_traffic(args.workload)
+    if tr is not None:
+        roofline["traffic"] = tr["dram_bytes_per_call"]
+        roofline["traffic_source"] = tr["source"]
+        roofline["kernel_us_ncu"] = tr.get("kernel_us")
+    flops = algorithmic_flops(w)
+    if flops:
+        # lower bound on the tensor-core rate of the score stage: all of the step time charged to it
+        roofline["tensor"] = {"algorithmic_flops_per_launch": flops, "achieved_tflops_lower_bound": flops / (ms_per_step * 1e-3) / 1e12,
+                              "peak_tflops": peaks["bf16_tflops"], "unit": "TFLOP/s"}
 
     # ---------------- e2e: pinned host K/V in, compacted K'/V' out, through the press API ---------
     e2e = None

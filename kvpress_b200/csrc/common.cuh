@@ -15,7 +15,7 @@ constexpr int kTile = 256;          // positions per select/compact tile (one pe
 constexpr int kTileThreads = 256;
 constexpr int kSfxStride = 264;     // u16 per tile record: sfx[0..256], gt_hi at [257], padding
 constexpr uint16_t kForcedKey = 0xFFFFu;  // ordered key of a forced-keep position
-constexpr int kFinalizeTiles = 4;          // 256-position tiles per CTA of the finalize kernels
+constexpr int kFinalizeTiles = 1;          // 256-position tiles per CTA of the finalize kernels (1: >5 waves at 128k, no tail)
 constexpr int kScoreChunkGeneric = 256;   // positions per CTA of the plain streaming score kernels
 // counters[] layout: [0] ticket, [1, 1+R) refine done, [1+R, 1+2R) row ready, then the slot below:
 // order-preserving uint image of the largest valid score (for the reference's max+1 sentinel);

@@ -21,3 +21,16 @@ tot = sum(a[1] for a in agg.values())
 print("---- per kernel (avg per launch, share of listed time)")
 for k, a in agg.items():
     print(f"{k:48s} n={a[0]:3d} {a[1] / a[0]:8.1f} us  read {a[2] / a[0]:8.1f} MB write {a[3] / a[0]:8.1f} MB  share {100 * a[1] / tot:5.1f}%")
+
+# optional: python tools/ncu_launches.py launches.csv <workload> -> update profiles/traffic.json with the
+# per-call DRAM traffic (kernels of one compress call = one launch of each listed kvp kernel)
+if len(sys.argv) > 2:
+    import json, os
+    per_call = {k: (a[2] + a[3]) / a[0] * 1e6 for k, a in agg.items() if "at::" not in k and "elementwise" not in k}
+    times = {k: round(a[1] / a[0], 1) for k, a in agg.items() if "at::" not in k and "elementwise" not in k}
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[sys.argv[2]] = {"dram_bytes_per_call": int(sum(per_call.values())), "kernel_us": times,
+                         "source": "ncu launch list " + os.path.basename(sys.argv[1]) + " (dram__bytes_read.sum + dram__bytes_write.sum, --cache-control none)"}
+    json.dump(data, open(path, "w"), indent=1)
+    print("traffic.json updated for", sys.argv[2], data[sys.argv[2]]["dram_bytes_per_call"] / 1e6, "MB")
