@@ -20,6 +20,8 @@
 //          dtype, keys + histogram for the select stage.
 // Both MMA kernels are persistent (one CTA per SM), warp-specialised: TMA producer, MMA issuer, TMEM
 // allocator, two epilogue warpgroups draining two TMEM accumulator buffers.
+#include <type_traits>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -218,16 +220,15 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
                     const uint32_t tbase = tmem + lane_base + buf * kBufCols + ch * kHalfCols;
                     uint32_t y[2][16];
                     umma::tmem_ld16(tbase, y[0]);
+                    // running max is kept in RAW logit units (q.k); c > 0 so the order is the same and the
+                    // scale folds into one FFMA per element: exp2(fma(y, c, -m*c))
                     float m = run_m[slot], z = run_z[slot];
-#pragma unroll
-                    for (int cc = 0; cc < kHalfCols / 16; ++cc) {
-                        umma::tmem_ld_wait();
-                        if (cc + 1 < kHalfCols / 16) umma::tmem_ld16(tbase + (cc + 1) * 16, y[(cc + 1) & 1]);
+                    auto chunk = [&](const uint32_t (&yy)[16], int cc, auto masked) {
                         float v[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            v[j] = __uint_as_float(y[cc & 1][j]) * c;
-                            if (!interior) {
+                            v[j] = __uint_as_float(yy[j]);
+                            if (decltype(masked)::value) {
                                 const int pos = key0 + cc * 16 + j;
                                 if (pos > limit || pos >= S) v[j] = -INFINITY;
                             }
@@ -241,16 +242,33 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
                         const float cmax = fmaxf(fmaxf(m4[0], m4[2]), fmaxf(m4[1], m4[3]));
                         const float m_new = fmaxf(m, cmax);
                         if (m_new > -INFINITY) {
+                            const float neg = -m_new * c;
                             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four independent sum chains
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
-                                a0 += fast_exp2(v[j] - m_new);
-                                a1 += fast_exp2(v[j + 1] - m_new);
-                                a2 += fast_exp2(v[j + 2] - m_new);
-                                a3 += fast_exp2(v[j + 3] - m_new);
+                                a0 += fast_exp2(fmaf(v[j], c, neg));
+                                a1 += fast_exp2(fmaf(v[j + 1], c, neg));
+                                a2 += fast_exp2(fmaf(v[j + 2], c, neg));
+                                a3 += fast_exp2(fmaf(v[j + 3], c, neg));
                             }
-                            z = z * fast_exp2(m - m_new) + ((a0 + a1) + (a2 + a3));
+                            z = z * fast_exp2((m - m_new) * c) + ((a0 + a1) + (a2 + a3));
                             m = m_new;
+                        }
+                    };
+                    // warp-uniform split: interior tiles (all but the last one or two) carry no mask code
+                    if (interior) {
+#pragma unroll
+                        for (int cc = 0; cc < kHalfCols / 16; ++cc) {
+                            umma::tmem_ld_wait();
+                            if (cc + 1 < kHalfCols / 16) umma::tmem_ld16(tbase + (cc + 1) * 16, y[(cc + 1) & 1]);
+                            chunk(y[cc & 1], cc, std::false_type{});
+                        }
+                    } else {
+#pragma unroll
+                        for (int cc = 0; cc < kHalfCols / 16; ++cc) {
+                            umma::tmem_ld_wait();
+                            if (cc + 1 < kHalfCols / 16) umma::tmem_ld16(tbase + (cc + 1) * 16, y[(cc + 1) & 1]);
+                            chunk(y[cc & 1], cc, std::true_type{});
                         }
                     }
                     run_m[slot] = m;
@@ -269,7 +287,7 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
                     // several Q blocks: the block's buffer is fixed, two column halves
                     const int p_idx = (kQHalves == 1) ? (part * 4 + wg * 2 + ch) : (part * 2 + ch);
                     sc.partial[((size_t)row * NQ + r) * n_parts + p_idx] =
-                        make_float2(run_m[qh >> 1], run_z[qh >> 1]);
+                        make_float2(run_m[qh >> 1] * c, run_z[qh >> 1]);  // (max in log2 units, sum)
                 }
             }
         }
