@@ -152,7 +152,7 @@ int kvp_launches_per_compress(const kvp_problem* p, int scorer, int* launches_ou
         case KVP_SCORER_KNORM:  // memset + (fused | score, select+compact)
             *launches_out = ((size_t)p->B * p->Hkv * p->S * p->D * 2 <= ((size_t)32 << 20)) ? 2 : 3;
             break;
-        case KVP_SCORER_SNAPKV: *launches_out = 7; break;  // memset, stats, combine, memset, colsum, finalize, select+compact
+        case KVP_SCORER_SNAPKV: *launches_out = 6; break;  // memset, stats, memset, colsum, finalize, select+compact
         case KVP_SCORER_EXPECTED_ATTENTION: *launches_out = 4; break;  // memset, logits, finalize, select+compact
         default: return KVP_ERR_BAD_ARGUMENT;
     }

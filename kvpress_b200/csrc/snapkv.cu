@@ -12,7 +12,7 @@
 // Here K is streamed twice through TMA (second time mostly from L2) and never expanded:
 //   pass 1 (snap_stats_kernel)  D[qrow, key] = Q_half[128 x d] * K_tile^T : thread = query row keeps an
 //          online (max, sum exp2) over its row -> per-CTA partials;
-//   combine (snap_combine_kernel): exact per-row normalisers -> bias_r = (-m_r + log2(1/Z_r)) / c;
+//   (each pass-2 CTA first merges the partials into the exact normalisers: bias_r = (-m_r - log2 Z_r) / c)
 //   pass 2 (snap_colsum_kernel) D[key, qrow] = K_tile[128 x d] * Q^T + 1 * bias^T (bias enters the MMA
 //          as an extra K=16 step, hi/lo split): thread = key sums exp2(c * D) over its NQ columns
 //          = sum_r p[r, j] -> fp32 pre-pool scores;
@@ -40,7 +40,6 @@ __device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2, 2 ulp; exp2(
 
 struct SnapScratch {
     float2* partial;  // [R][NQ][n_parts]  (max, sum) in the log2 domain
-    float* qbias;     // [R][NQ]           (-m + log2(1/Z)) / c
     float* colsum;    // [R][S_pad]        sum_r p[r, j]
 };
 
@@ -50,8 +49,7 @@ size_t snapkv_scratch_bytes(const Dims& d, int window) {
     const int G = d.Hq / d.H;
     const size_t NQ = (size_t)G * window;
     const size_t S_pad = (size_t)((d.S + kTile - 1) / kTile) * kTile;
-    return sn_align((size_t)d.R * NQ * kSnMaxParts * sizeof(float2)) + sn_align((size_t)d.R * NQ * 4) +
-           sn_align((size_t)d.R * S_pad * 4);
+    return sn_align((size_t)d.R * NQ * kSnMaxParts * sizeof(float2)) + sn_align((size_t)d.R * S_pad * 4);
 }
 
 static SnapScratch carve_snap(const Dims& d, int window, const Workspace& ws) {
@@ -61,8 +59,6 @@ static SnapScratch carve_snap(const Dims& d, int window, const Workspace& ws) {
     SnapScratch s;
     s.partial = reinterpret_cast<float2*>(p);
     p += sn_align((size_t)d.R * NQ * kSnMaxParts * sizeof(float2));
-    s.qbias = reinterpret_cast<float*>(p);
-    p += sn_align((size_t)d.R * NQ * 4);
     s.colsum = reinterpret_cast<float*>(p);
     return s;
 }
@@ -297,28 +293,12 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
     if (warp == 2) umma::tmem_dealloc(tmem, 256);
 }
 
-// ---- combine: exact normalisers -> the bias the second pass feeds through the MMA --------------------
-__global__ void snap_combine_kernel(int NQ, int n_parts, float inv_c, SnapScratch sc, int total) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (row, qrow)
-    if (i >= total) return;
-    float m = -INFINITY, z = 0.f;
-    for (int p = 0; p < n_parts; ++p) {
-        const float2 pz = sc.partial[(size_t)i * n_parts + p];
-        const float mn = fmaxf(m, pz.x);
-        z = (mn == -INFINITY) ? 0.f : z * exp2f(m - mn) + pz.y * exp2f(pz.x - mn);
-        m = mn;
-    }
-    // p[r, j] = exp2(c*y - m) / Z = exp2(c * (y + bias)),  bias = (-m - log2 Z) / c
-    sc.qbias[i] = (-m - log2f(z)) * inv_c;
-    (void)NQ;
-}
-
 // ---- pass 2: normalised column sums --------------------------------------------------------------------
 template <typename T, int D, int NQP>
 __global__ void __launch_bounds__(kSnThreads, 1)
 snap_colsum_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapQ, int H,
-                   int G, int S, int window, int R, int n_tiles128, int ctas_per_row, SnapScratch sc,
-                   int S_pad) {
+                   int G, int S, int window, int R, int n_tiles128, int ctas_per_row, int n_parts,
+                   SnapScratch sc, int S_pad) {
     using L = SnSmem<D, NQP>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(
@@ -376,8 +356,20 @@ snap_colsum_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_consta
         __syncthreads();
         // bias operand (hi/lo split) and the ones operand, both in the no-swizzle K=16 layout
         for (int n = tid; n < NQP; n += kSnThreads) {
+            // exact normaliser of query row n from the per-CTA partials of pass 1:
+            // p[n, j] = exp2(c*y - m) / Z = exp2(c * (y + bias)),  bias = (-m - log2 Z) / c
             float bias = 0.f;
-            if (n < NQ) bias = sc.qbias[(size_t)row * NQ + n];
+            if (n < NQ) {
+                float m = -INFINITY, z = 0.f;
+                const float2* part_n = sc.partial + ((size_t)row * NQ + n) * n_parts;
+                for (int pp = 0; pp < n_parts; ++pp) {
+                    const float2 pz = part_n[pp];
+                    const float mn = fmaxf(m, pz.x);
+                    z = (mn == -INFINITY) ? 0.f : z * fast_exp2(m - mn) + pz.y * fast_exp2(pz.x - mn);
+                    m = mn;
+                }
+                bias = (-m - log2f(z)) / c;
+            }
             const uint16_t hi = F16Traits<T>::from_float(bias);
             const uint16_t lo = F16Traits<T>::from_float(bias - F16Traits<T>::to_float(hi));
             *reinterpret_cast<uint4*>(s_bx + umma::k16_noswizzle_offset(n, 0)) =
@@ -617,14 +609,10 @@ static cudaError_t launch_snap_t(const Dims& d, int dtype, const void* K, const 
     k1<<<grid, kSnThreads, smem, st>>>(mapK, mapQ, d.H, G, d.S, window, d.R, n_tiles128, ctas_per_row,
                                        n_parts, sc);
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return e;
-    const int total = d.R * NQ;
-    const float inv_c = sqrtf((float)D) / kLog2e;
-    snap_combine_kernel<<<(total + 127) / 128, 128, 0, st>>>(NQ, n_parts, inv_c, sc, total);
-    if ((e = cudaPeekAtLastError()) != cudaSuccess) return e;
     e = cudaMemsetAsync(sc.colsum, 0, (size_t)d.R * ws.S_pad * 4, st);  // warpgroups add their halves
     if (e != cudaSuccess) return e;
-    k2<<<grid, kSnThreads, smem, st>>>(mapK, mapQ, d.H, G, d.S, window, d.R, n_tiles128, ctas_per_row, sc,
-                                       ws.S_pad);
+    k2<<<grid, kSnThreads, smem, st>>>(mapK, mapQ, d.H, G, d.S, window, d.R, n_tiles128, ctas_per_row, n_parts,
+                                       sc, ws.S_pad);
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return e;
     dim3 grid3((ws.n_tiles + kFinalizeTiles - 1) / kFinalizeTiles, d.R);
     snap_finalize_kernel<T><<<grid3, kTileThreads, 0, st>>>(d.S, window, kernel_size, 1.0f / (float)NQ, sc, ws,
