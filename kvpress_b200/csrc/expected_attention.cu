@@ -86,7 +86,7 @@ template <typename T, int D, int G>
 __global__ void __launch_bounds__(kEaThreads, 1)
 ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapCov,
                  const T* __restrict__ mu, int H, int Hq, int S, int n_sink, int R, int n_tiles128,
-                 int ctas_per_row, int n_parts, EaScratch sc, int S_pad) {
+                 int ctas_per_row, int n_parts, EaScratch sc, int S_pad, int g_total, int g_off) {
     using L = EaSmem<D, G>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // dynamic shared memory is only guaranteed 16-B aligned: round up to 1024 B for the swizzle
@@ -153,7 +153,8 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
 
     for (int row = group; row < R; row += n_groups) {
         const int b = row / H, h = row % H;
-        const int hq0 = b * Hq + h * G;  // first query head of this kv head in [B*Hq]
+        // this launch covers query heads [g_off, g_off + G) of the kv head's g_total heads
+        const int hq0 = b * Hq + h * g_total + g_off;  // first of them in [B*Hq]
         __syncthreads();  // previous row fully drained (s_bias, s_cov, s_red reusable)
         for (int n = tid; n < G * D; n += kEaThreads) {
             const float bias = bias_scale * F16Traits<T>::to_float(
@@ -331,7 +332,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                         const int g = half * HPH + q;
                         const float lg = acc[q] * inv_2d;
                         if (valid && g < G) {
-                            sc.logits[((size_t)row * G + g) * S_pad + s] = lg;
+                            sc.logits[((size_t)row * g_total + g_off + g) * S_pad + s] = lg;
                             const float m_new = fmaxf(run_m[q], lg);
                             run_z[q] = run_z[q] * __expf(run_m[q] - m_new) + __expf(lg - m_new);
                             run_m[q] = m_new;
@@ -373,7 +374,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                 z = (mn == -INFINITY) ? 0.f : z * __expf(m - mn) + z2 * __expf(m2 - mn);
                 m = mn;
             }
-            sc.partial[((size_t)row * G + g) * n_parts + part] = make_float2(m, z);
+            sc.partial[((size_t)row * g_total + g_off + g) * n_parts + part] = make_float2(m, z);
         }
     }
 
@@ -499,63 +500,64 @@ ea_finalize_kernel(const T* __restrict__ V, Strides3 vs, int H, int D, int G, in
     __shared__ uint32_t shist[256];
     __shared__ float s_m[8], s_iz[8];
     __shared__ float s_max[8];
+    static_assert(kFinalizeTiles == 1, "one 256-position tile per CTA");
     const int tile = blockIdx.x, row = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     shist[tid] = 0;
+    const int s = tile * kTile + tid;
+    const bool scored = (s < S) && (s >= n_sink);
+    // 1. independent loads first: this position's logits and (warps < G) the per-CTA softmax partials
+    float lg[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+        lg[g] = (g < G && scored) ? __ldcg(&sc.logits[((size_t)row * G + g) * ws.S_pad + s]) : 0.f;
+    float pm = -INFINITY, pz = 0.f;
     if (warp < G) {
-        float m = -INFINITY, z = 0.f;
         for (int p = lane; p < n_parts; p += 32) {
-            const float2 pz = sc.partial[((size_t)row * G + warp) * n_parts + p];
-            const float mn = fmaxf(m, pz.x);
-            z = (mn == -INFINITY) ? 0.f : z * __expf(m - mn) + pz.y * __expf(pz.x - mn);
-            m = mn;
+            const float2 q = sc.partial[((size_t)row * G + warp) * n_parts + p];
+            const float mn = fmaxf(pm, q.x);
+            pz = (mn == -INFINITY) ? 0.f : pz * __expf(pm - mn) + q.y * __expf(q.x - mn);
+            pm = mn;
         }
+    }
+    // 2. the streaming pass over V (||v_s|| for this tile), overlapping the loads above
+    if (use_vnorm) row_norm_chunk<T, LPR>(V, vs, row / H, row % H, tile, S, D, s_vnorm);
+    // 3. exact softmax normalisers of the G heads
+    if (warp < G) {
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
-            const float m2 = __shfl_xor_sync(0xFFFFFFFFu, m, off);
-            const float z2 = __shfl_xor_sync(0xFFFFFFFFu, z, off);
-            const float mn = fmaxf(m, m2);
-            z = (mn == -INFINITY) ? 0.f : z * __expf(m - mn) + z2 * __expf(m2 - mn);
-            m = mn;
+            const float m2 = __shfl_xor_sync(0xFFFFFFFFu, pm, off);
+            const float z2 = __shfl_xor_sync(0xFFFFFFFFu, pz, off);
+            const float mn = fmaxf(pm, m2);
+            pz = (mn == -INFINITY) ? 0.f : pz * __expf(pm - mn) + z2 * __expf(m2 - mn);
+            pm = mn;
         }
         if (lane == 0) {
-            s_m[warp] = m;
-            s_iz[warp] = 1.0f / z;
+            s_m[warp] = pm;
+            s_iz[warp] = 1.0f / pz;
         }
     }
     __syncthreads();
-    if (use_vnorm) {  // ||v_s|| for this CTA's positions: one streaming pass over V, no barriers inside
-        for (int sub = 0; sub < kFinalizeTiles; ++sub) {
-            const int t = tile * kFinalizeTiles + sub;
-            if (t < ws.n_tiles) row_norm_chunk<T, LPR>(V, vs, row / H, row % H, t, S, D, s_vnorm + sub * kTile);
-        }
-        __syncthreads();
-    }
     float fmax_valid = -INFINITY;
-    for (int sub = 0; sub < kFinalizeTiles; ++sub) {
-        const int t = tile * kFinalizeTiles + sub;
-        if (t >= ws.n_tiles) break;
-        const int s = t * kTile + tid;
-        uint16_t bits = 0, key = 0;
-        if (s < S) {
-            if (s < n_sink) {
-                key = kForcedKey;
-            } else {
-                float p = 0.f;
-                for (int g = 0; g < G; ++g)
-                    p += __expf(sc.logits[((size_t)row * G + g) * ws.S_pad + s] - s_m[g]) * s_iz[g];
-                p *= (1.0f / (float)G);
-                const float score = use_vnorm ? (p + eps) * s_vnorm[sub * kTile + tid] : p;
-                bits = F16Traits<T>::from_float(score);
-                key = ordered_key16(bits, F16Traits<T>::kInfBits);
-                fmax_valid = fmaxf(fmax_valid, F16Traits<T>::to_float(bits));
-            }
+    uint16_t bits = 0, key = 0;
+    if (s < S) {
+        if (!scored) {
+            key = kForcedKey;
+        } else {
+            float p = 0.f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                if (g < G) p += __expf(lg[g] - s_m[g]) * s_iz[g];
+            p *= (1.0f / (float)G);
+            const float score = use_vnorm ? (p + eps) * s_vnorm[tid] : p;
+            bits = F16Traits<T>::from_float(score);
+            key = ordered_key16(bits, F16Traits<T>::kInfBits);
+            fmax_valid = F16Traits<T>::to_float(bits);
         }
-        __syncthreads();  // previous sub-tile's staging buffers are free
-        skeys[tid] = key;
-        sscores[tid] = bits;
-        __syncthreads();
-        flush_chunk_keys<1, false>(skeys, sscores, shist, row, t * kTile, S, ws, scores_out);
     }
+    skeys[tid] = key;
+    sscores[tid] = bits;
+    __syncthreads();
+    flush_chunk_keys<1, false>(skeys, sscores, shist, row, tile * kTile, S, ws, scores_out);
     // max over valid scores of the whole tensor (for the reference's max+1 sentinel)
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1)
@@ -606,7 +608,7 @@ cudaError_t launch_fill_sentinel(int dtype, void* scores_out, int R, int S, int 
 template <typename T, int D, int G>
 static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* mu, const void* cov,
                                       int n_sink, const Workspace& ws, const EaScratch& sc,
-                                      int* n_parts_out, cudaStream_t st) {
+                                      int* n_parts_out, cudaStream_t st, int g_off = 0) {
     using L = EaSmem<D, G>;
     static int sm_count = 0;
     if (sm_count == 0) {
@@ -648,7 +650,7 @@ static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kEaThreads, smem, st>>>(mapK, mapCov, static_cast<const T*>(mu), d.H, d.Hq, d.S, n_sink, d.R,
-                                         n_tiles128, ctas_per_row, ctas_per_row, sc, ws.S_pad);
+                                         n_tiles128, ctas_per_row, ctas_per_row, sc, ws.S_pad, d.Hq / d.H, g_off);
     return cudaPeekAtLastError();
 }
 
@@ -670,7 +672,12 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
         else if (d.D == 64 && G == 1) e = launch_ea_logits_t<T, 64, 1>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
         else if (d.D == 64 && G == 2) e = launch_ea_logits_t<T, 64, 2>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
         else if (d.D == 64 && G == 4) e = launch_ea_logits_t<T, 64, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
-        else return cudaErrorNotSupported;
+        else if (G == 8 && (d.D == 128 || d.D == 64)) {
+            // eight query heads per kv head (Llama-3.1-70B): two launches of four resident Sigma each
+            for (int g_off = 0; g_off < 8 && e == cudaSuccess; g_off += 4)
+                e = (d.D == 128) ? launch_ea_logits_t<T, 128, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st, g_off)
+                                 : launch_ea_logits_t<T, 64, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st, g_off);
+        } else return cudaErrorNotSupported;
     } else {
         n_parts = (d.S + kScoreChunkGeneric - 1) / kScoreChunkGeneric;
         dim3 grid(n_parts, d.R);

@@ -350,3 +350,95 @@ def test_snapkv_model_shapes_vs_fp32_oracle(Hq, Hkv, S):
     ref = O.snapkv_scores(q, k, w, 5)
     _assert_scores_close(scores.cpu(), ref, hi, slice(S - w, S), torch.bfloat16)
     assert torch.equal(idx.cpu().long(), O.select_lowest_index_ties(scores.cpu(), n_kept))
+
+
+# ---------------------------------------------------------------------------------------------------
+# full BASELINE sizes: size-independent properties (an element-wise CPU oracle would take minutes)
+# ---------------------------------------------------------------------------------------------------
+def _gather_dev(x, idx):
+    return x.gather(2, idx.long().unsqueeze(-1).expand(-1, -1, -1, x.shape[-1]))
+
+
+def _assert_topk_of_own_scores(scores, idx, n_kept, forced: slice):
+    """kept scores == the n_kept largest scores (as multisets), forced positions all kept."""
+    s = scores.float().clone()
+    s[..., forced] = float("inf")
+    kept = s.gather(2, idx.long()).sort(-1).values
+    top = s.sort(-1).values[..., -n_kept:]
+    assert torch.equal(kept, top)
+    idxl = idx.long()
+    assert (idxl[..., 1:] > idxl[..., :-1]).all()
+
+
+def test_expected_attention_128k_properties():
+    """BASELINE configs[2]: ExpectedAttentionPress r=0.7, Llama-3.1-8B layer shape, 128k context."""
+    nat = _native()
+    torch.manual_seed(41)
+    B, H, Hq, S, D = 1, 8, 32, 131072, 128
+    k = torch.randn(B, H, S, D, dtype=torch.bfloat16, device=DEV)
+    v = torch.randn(B, H, S, D, dtype=torch.bfloat16, device=DEV)
+    mu = (0.5 * torch.randn(B, Hq, D, device=DEV)).to(torch.bfloat16)
+    a = torch.randn(B, Hq, D, D, device=DEV) / D ** 0.5
+    cov = (a @ a.transpose(-1, -2)).to(torch.bfloat16)
+    n_kept = O.kept_count(S, 0.7)
+    assert n_kept == 39321
+    k_out, v_out, idx, scores = nat.expected_attention_compress(k, v, mu, cov, 0.0, 4, True, n_kept,
+                                                                return_indices=True, return_scores=True)
+    assert torch.equal(k_out, _gather_dev(k, idx)) and torch.equal(v_out, _gather_dev(v, idx))
+    _assert_topk_of_own_scores(scores, idx, n_kept, slice(0, 4))
+    assert (idx[..., :4] == torch.arange(4, device=DEV)).all()
+    # spot-check the scores of one kv head on a 4k slice against the fp32 formula evaluated by torch on the GPU
+    h, sl = 3, slice(60000, 64096)
+    kk = k[0, h].float()
+    lg = torch.stack([(kk @ mu[0, 4 * h + g].float()) / D ** 0.5
+                      + ((kk @ cov[0, 4 * h + g].float()) * kk).sum(-1) / (2 * D) for g in range(4)])
+    lg = lg[:, 4:]
+    p = torch.softmax(lg, dim=-1).mean(0) * v[0, h, 4:].float().norm(dim=-1)
+    got = scores[0, h, 4:].float()
+    rel = ((got - p).abs() / p.clamp_min(1e-30))[sl]
+    assert rel.max() < 2 ** -7
+
+
+def test_snapkv_32k_and_128k_properties():
+    """BASELINE configs[1] (32k, Hq=32) and the per-layer shape of configs[4] (128k, Hq=64)."""
+    nat = _native()
+    for Hq, S in ((32, 32768), (64, 131072)):
+        torch.manual_seed(43 + Hq)
+        B, H, D, w = 1, 8, 128, 64
+        k = torch.randn(B, H, S, D, dtype=torch.bfloat16, device=DEV)
+        v = torch.randn(B, H, S, D, dtype=torch.bfloat16, device=DEV)
+        q = (torch.randn(B, Hq, w, D, device=DEV) * 1.5).to(torch.bfloat16)
+        n_kept = O.kept_count(S, 0.5)
+        k_out, v_out, idx, scores = nat.snapkv_compress(k, v, q, w, 5, n_kept, return_indices=True,
+                                                        return_scores=True)
+        assert torch.equal(k_out, _gather_dev(k, idx)) and torch.equal(v_out, _gather_dev(v, idx))
+        _assert_topk_of_own_scores(scores, idx, n_kept, slice(S - w, S))
+        assert (idx[..., -w:] == torch.arange(S - w, S, device=DEV)).all()
+        # pre-pool column sums of one kv head against torch (fp32) on the GPU, then the 5-tap box filter
+        h, G = 5, Hq // H
+        qq = q[0, h * G:(h + 1) * G].reshape(G * w, D).float()
+        logits = (qq @ k[0, h].float().T) / D ** 0.5
+        i = torch.arange(G * w, device=DEV) % w
+        mask = torch.arange(S, device=DEV)[None, :] > (S - w + i)[:, None]
+        p = torch.softmax(logits.masked_fill(mask, float("-inf")), dim=-1)[:, : S - w]
+        col = p.reshape(G, w, -1).mean(1)
+        pooled = torch.nn.functional.avg_pool1d(col[None], 5, stride=1, padding=2)[0].mean(0)
+        got = scores[0, h, : S - w].float()
+        rel = (got - pooled).abs() / pooled.clamp_min(1e-30)
+        assert rel.max() < 2 ** -7
+
+
+def test_expected_attention_eight_heads_per_kv_head():
+    """Llama-3.1-70B grouping (Hq/Hkv = 8): two four-head launches of the tensor-core kernel."""
+    nat = _native()
+    torch.manual_seed(47)
+    B, H, Hq, S, D = 1, 2, 16, 3000, 128
+    k = torch.randn(B, H, S, D, dtype=torch.bfloat16)
+    v = torch.randn(B, H, S, D, dtype=torch.bfloat16)
+    mu = (0.5 * torch.randn(B, Hq, D)).to(torch.bfloat16)
+    a = torch.randn(B, Hq, D, D) / D ** 0.5
+    cov = (a @ a.transpose(-1, -2)).to(torch.bfloat16)
+    got = nat.expected_attention_score(k.to(DEV), v.to(DEV), mu.to(DEV), cov.to(DEV), 0.0, 4, True).cpu()
+    hi = O.expected_attention_scores_fp32(k, v, mu, cov, 0.0, 4, True)
+    ref = O.expected_attention_scores(k, v, mu, cov, 0.0, 4, True)
+    _assert_scores_close(got, ref, hi, slice(0, 4), torch.bfloat16)
