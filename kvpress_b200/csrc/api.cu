@@ -153,7 +153,7 @@ int kvp_launches_per_compress(const kvp_problem* p, int scorer, int* launches_ou
             *launches_out = ((size_t)p->B * p->Hkv * p->S * p->D * 2 <= ((size_t)32 << 20)) ? 2 : 3;
             break;
         case KVP_SCORER_SNAPKV: *launches_out = 6; break;  // memset, stats, memset, colsum, finalize, select+compact
-        case KVP_SCORER_EXPECTED_ATTENTION: *launches_out = 4; break;  // memset, logits, finalize, select+compact
+        case KVP_SCORER_EXPECTED_ATTENTION: *launches_out = 5; break;  // memset, logits, vnorm (side stream), finalize, select+compact
         default: return KVP_ERR_BAD_ARGUMENT;
     }
     return KVP_OK;

@@ -18,6 +18,8 @@
 //   kernel 2 (ea_finalize_kernel): combines the per-CTA softmax statistics, forms the final score in
 //       fp32, rounds it ONCE to the cache dtype, and emits keys + histogram for the select stage.
 // Covariance-free mode (use_covariance=False) is a plain streaming GEMV kernel.
+#include <mutex>
+
 #include "common.cuh"
 #include "knorm_chunk.cuh"
 #include "umma.cuh"
@@ -39,6 +41,7 @@ constexpr int kEaMaxParts = 160;  // upper bound on CTAs per (b,h) row (>= SM co
 
 struct EaScratch {
     float* logits;    // [R][G][S_pad]
+    float* vnorm;     // [R][S_pad]
     float2* partial;  // [R][G][n_parts] (max, sum exp) per CTA part
 };
 
@@ -49,7 +52,8 @@ size_t ea_scratch_bytes(const Dims& d) {
     const size_t S_pad = (size_t)((d.S + kTile - 1) / kTile) * kTile;
     const size_t n_parts = (size_t)((d.S + kScoreChunkGeneric - 1) / kScoreChunkGeneric);
     const size_t parts = n_parts > kEaMaxParts ? n_parts : kEaMaxParts;
-    return align256((size_t)d.R * G * S_pad * 4) + align256((size_t)d.R * G * parts * sizeof(float2));
+    return align256((size_t)d.R * G * S_pad * 4) + align256((size_t)d.R * S_pad * 4) +
+           align256((size_t)d.R * G * parts * sizeof(float2));
 }
 
 static EaScratch carve_ea(const Dims& d, const Workspace& ws) {
@@ -59,6 +63,8 @@ static EaScratch carve_ea(const Dims& d, const Workspace& ws) {
     EaScratch s;
     s.logits = reinterpret_cast<float*>(p);
     p += align256((size_t)d.R * G * S_pad * 4);
+    s.vnorm = reinterpret_cast<float*>(p);
+    p += align256((size_t)d.R * S_pad * 4);
     s.partial = reinterpret_cast<float2*>(p);
     return s;
 }
@@ -82,8 +88,10 @@ struct EaSmem {
     static_assert(kTotal + 1024 <= 227 * 1024, "shared memory budget");
 };
 
+// __launch_bounds__(512): ptxas keeps the kernel at <= 128 registers/thread (it is launched with
+// kEaThreads = 384), leaving 16 K registers per SM for a co-resident ea_vnorm_kernel CTA.
 template <typename T, int D, int G>
-__global__ void __launch_bounds__(kEaThreads, 1)
+__global__ void __launch_bounds__(512, 1)
 ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapCov,
                  const T* __restrict__ mu, int H, int Hq, int S, int n_sink, int R, int n_tiles128,
                  int ctas_per_row, int n_parts, EaScratch sc, int S_pad, int g_total, int g_off) {
@@ -488,13 +496,25 @@ ea_mu_logits_kernel(const T* __restrict__ K, Strides3 ks, const T* __restrict__ 
     }
 }
 
-// ---- finalize: softmax normalisation, group mean, * ||v||, ONE rounding, keys + histogram -----------
+// ---- ||v_s||_2 for every position: plain streaming kernel, launched on a side stream so that it shares
+// the SMs with the tensor-bound logits kernel (which leaves ~70 % of the HBM bandwidth idle) -----------
 template <typename T, int LPR>
+__global__ void __launch_bounds__(kTileThreads, 4)
+ea_vnorm_kernel(const T* __restrict__ V, Strides3 vs, int H, int S, int D, float* __restrict__ vnorm,
+                int S_pad) {
+    __shared__ float s_norm[kTile];
+    const int tile = blockIdx.x, row = blockIdx.y, tid = threadIdx.x;
+    row_norm_chunk<T, LPR>(V, vs, row / H, row % H, tile, S, D, s_norm);
+    __syncthreads();
+    const int s = tile * kTile + tid;
+    if (s < S) vnorm[(size_t)row * S_pad + s] = s_norm[tid];
+}
+
+// ---- finalize: softmax normalisation, group mean, * ||v||, ONE rounding, keys + histogram -----------
+template <typename T>
 __global__ void __launch_bounds__(kTileThreads)
-ea_finalize_kernel(const T* __restrict__ V, Strides3 vs, int H, int D, int G, int S, int n_sink,
-                   int use_vnorm, float eps, int n_parts, EaScratch sc, Workspace ws,
-                   uint16_t* __restrict__ scores_out) {
-    __shared__ float s_vnorm[kFinalizeTiles * kTile];
+ea_finalize_kernel(int G, int S, int n_sink, int use_vnorm, float eps, int n_parts, EaScratch sc,
+                   Workspace ws, uint16_t* __restrict__ scores_out) {
     __shared__ uint16_t skeys[kTile];
     __shared__ uint16_t sscores[kTile];
     __shared__ uint32_t shist[256];
@@ -519,8 +539,7 @@ ea_finalize_kernel(const T* __restrict__ V, Strides3 vs, int H, int D, int G, in
             pm = mn;
         }
     }
-    // 2. the streaming pass over V (||v_s|| for this tile), overlapping the loads above
-    if (use_vnorm) row_norm_chunk<T, LPR>(V, vs, row / H, row % H, tile, S, D, s_vnorm);
+    const float vn = (use_vnorm && scored) ? __ldcg(&sc.vnorm[(size_t)row * ws.S_pad + s]) : 1.f;
     // 3. exact softmax normalisers of the G heads
     if (warp < G) {
 #pragma unroll
@@ -548,7 +567,7 @@ ea_finalize_kernel(const T* __restrict__ V, Strides3 vs, int H, int D, int G, in
             for (int g = 0; g < 8; ++g)
                 if (g < G) p += __expf(lg[g] - s_m[g]) * s_iz[g];
             p *= (1.0f / (float)G);
-            const float score = use_vnorm ? (p + eps) * s_vnorm[tid] : p;
+            const float score = use_vnorm ? (p + eps) * vn : p;
             bits = F16Traits<T>::from_float(score);
             key = ordered_key16(bits, F16Traits<T>::kInfBits);
             fmax_valid = F16Traits<T>::to_float(bits);
@@ -654,6 +673,45 @@ static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* 
     return cudaPeekAtLastError();
 }
 
+// Side stream + fork/join events for the concurrent V-norm kernel: created once per device, never
+// modified afterwards (the only process-wide state of the library besides cached device properties).
+struct EaSideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok = false;
+};
+static EaSideStream* ea_side_stream() {
+    static EaSideStream per_device[64];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    EaSideStream& s = per_device[dev];
+    if (!s.ok) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        s.ok = true;
+    }
+    return &s;
+}
+
+template <typename T>
+static cudaError_t launch_ea_vnorm_t(const Dims& d, const void* V, const Workspace& ws, const EaScratch& sc,
+                                     cudaStream_t st) {
+    dim3 grid(ws.n_tiles, d.R);
+    const int nvec = d.D / 8;
+#define KVP_EA_VN(LPR)                                                                               \
+    ea_vnorm_kernel<T, LPR><<<grid, kTileThreads, 0, st>>>(static_cast<const T*>(V), d.vs, d.H, d.S, d.D, \
+                                                           sc.vnorm, ws.S_pad)
+    if (nvec <= 4) KVP_EA_VN(4);
+    else if (nvec <= 8) KVP_EA_VN(8);
+    else if (nvec <= 16) KVP_EA_VN(16);
+    else KVP_EA_VN(32);
+#undef KVP_EA_VN
+    return cudaPeekAtLastError();
+}
+
 template <typename T>
 static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const void* V, const void* mu,
                                const void* cov, float eps, int n_sink, int use_vnorm,
@@ -664,6 +722,12 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
     const EaScratch sc = carve_ea(d, ws);
     int n_parts = 0;
     cudaError_t e = cudaSuccess;
+    // fork: the V-norm kernel only needs V; it runs on the side stream next to the logits kernel
+    EaSideStream* side = use_vnorm ? ea_side_stream() : nullptr;
+    if (side != nullptr) {
+        if ((e = cudaEventRecord(side->fork, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return e;
+    }
     if (cov != nullptr) {
         // tensor-core path: head_dim 64 or 128, up to 4 query heads per kv head resident in smem
         if (d.D == 128 && G == 1) e = launch_ea_logits_t<T, 128, 1>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
@@ -693,16 +757,18 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
         e = cudaPeekAtLastError();
     }
     if (e != cudaSuccess) return e;
+    if (use_vnorm) {
+        // launched AFTER the logits kernel so that its CTAs fill the resources the logits CTAs leave free
+        cudaStream_t vst = side != nullptr ? side->stream : st;
+        if ((e = launch_ea_vnorm_t<T>(d, V, ws, sc, vst)) != cudaSuccess) return e;
+        if (side != nullptr) {  // join
+            if ((e = cudaEventRecord(side->join, side->stream)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return e;
+        }
+    }
     dim3 grid2((ws.n_tiles + kFinalizeTiles - 1) / kFinalizeTiles, d.R);
-#define KVP_EA_FIN(LPR)                                                                                    \
-    ea_finalize_kernel<T, LPR><<<grid2, kTileThreads, 0, st>>>(static_cast<const T*>(V), d.vs, d.H, d.D, G, \
-                                                               d.S, n_sink, use_vnorm, eps, n_parts, sc, ws, \
-                                                               static_cast<uint16_t*>(scores_out))
-    if (nvec <= 4) KVP_EA_FIN(4);
-    else if (nvec <= 8) KVP_EA_FIN(8);
-    else if (nvec <= 16) KVP_EA_FIN(16);
-    else KVP_EA_FIN(32);
-#undef KVP_EA_FIN
+    ea_finalize_kernel<T><<<grid2, kTileThreads, 0, st>>>(G, d.S, n_sink, use_vnorm, eps, n_parts, sc, ws,
+                                                          static_cast<uint16_t*>(scores_out));
     e = cudaPeekAtLastError();
     if (e != cudaSuccess) return e;
     if (scores_out != nullptr) e = launch_fill_sentinel(dtype, scores_out, d.R, d.S, 0, n_sink, ws, st);
