@@ -29,7 +29,8 @@
  *     resolved towards the LOWEST position (deterministic; torch.topk leaves it unspecified).
  *   - Caller owns all memory (outputs + workspace of kvp_workspace_bytes()). The library
  *     allocates nothing, keeps no mutable global state, never synchronises the stream, and is
- *     re-entrant per (stream, workspace).
+ *     re-entrant per (stream, workspace). (ExpectedAttention enqueues its ||v|| kernel on an internal
+ *     per-device side stream joined back into the caller's stream before the call returns.)
  *   - Return value: KVP_OK (0) or a negative kvp_status. No exceptions cross this boundary.
  */
 #ifndef KVPRESS_B200_H

@@ -680,6 +680,7 @@ struct EaSideStream {
     cudaEvent_t fork = nullptr, join = nullptr;
     bool ok = false;
 };
+static std::mutex g_ea_enqueue_mu;  // serialises fork..join enqueues that share the side stream / events
 static EaSideStream* ea_side_stream() {
     static EaSideStream per_device[64];
     static std::mutex mu;
@@ -724,6 +725,10 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
     cudaError_t e = cudaSuccess;
     // fork: the V-norm kernel only needs V; it runs on the side stream next to the logits kernel
     EaSideStream* side = use_vnorm ? ea_side_stream() : nullptr;
+    // host threads enqueueing on different streams of one device share the side stream and its two
+    // events: hold the lock for the (host-only, microseconds) fork..join enqueue sequence
+    std::unique_lock<std::mutex> enqueue_lock(g_ea_enqueue_mu, std::defer_lock);
+    if (side != nullptr) enqueue_lock.lock();
     if (side != nullptr) {
         if ((e = cudaEventRecord(side->fork, st)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return e;
