@@ -43,6 +43,9 @@ WORKLOADS = {
                             label="SnapKVPress r=0.5, Llama-3.1-70B layer shape, 128k ctx"),
     "knorm_128k": dict(scorer="knorm", B=1, Hkv=8, Hq=8, S=131072, D=128, ratio=0.5, config_index=None,
                        label="KnormPress r=0.5, Llama-3.1-8B layer shape, 128k ctx"),
+    # KeyRerotationPress(KnormPress): score + select + compaction with re-rotated keys
+    "rerotate_knorm_128k": dict(scorer="knorm_rerotate", B=1, Hkv=8, Hq=8, S=131072, D=128, ratio=0.5,
+                                config_index=None, label="KeyRerotationPress(KnormPress) r=0.5, 128k ctx"),
     "streaming_128k": dict(scorer="streaming", B=1, Hkv=8, Hq=8, S=131072, D=128, ratio=0.5, config_index=None,
                            label="StreamingLLMPress r=0.5, 128k ctx"),
     # steady state of configs[3]: DecodingPress(Knorm, 512, 2048) compaction 2560 -> 2048
@@ -62,6 +65,7 @@ def algorithmic_bytes(w: dict, n_kept: int) -> int:
     S = w["S"]
     per_head = {
         "knorm": row * (S + 3 * n_kept),
+        "knorm_rerotate": row * (S + 3 * n_kept),
         "snapkv": row * (S + 3 * n_kept),
         "expected_attention": row * (2 * S + 2 * n_kept),
         "streaming": row * 4 * n_kept,
@@ -114,6 +118,8 @@ def make_inputs(w: dict, device, seed: int, pinned_host: bool = False):
         if pinned_host:
             K, V = K.pin_memory(), V.pin_memory()
     extra = {}
+    if w["scorer"] == "knorm_rerotate":
+        extra["inv_freq"] = 1.0 / (500000.0 ** (torch.arange(0, D, 2).float() / D))  # Llama-3 rope_theta
     if w["scorer"] == "snapkv":
         extra["q_window"] = torch.randn((B, Hq, 64, D), generator=g, dtype=torch.float32).to(torch.bfloat16)
     if w["scorer"] == "expected_attention":
@@ -131,6 +137,8 @@ def run_native(w: dict, K, V, extra, n_kept: int):
     s = w["scorer"]
     if s == "knorm":
         return native.knorm_compress(K, V, n_kept)[:2]
+    if s == "knorm_rerotate":
+        return native.scores_compress_rerotate(native.knorm_score(K), K, V, n_kept, extra["inv_freq"])[:2]
     if s == "streaming":
         return native.streaming_compress(K, V, n_kept, 4)[:2]
     if s == "snapkv":
@@ -146,6 +154,9 @@ def run_oracle(w: dict, K, V, extra, ratio: float):
     s = w["scorer"]
     if s == "knorm":
         return O.knorm_compress(K, V, ratio)
+    if s == "knorm_rerotate":
+        n_kept = O.kept_count(K.shape[2], ratio)
+        return O.key_rerotation_compress(O.knorm_scores(K), K, V, n_kept, extra["inv_freq"])[:2]
     if s == "streaming":
         return O.streaming_compress(K, V, ratio, 4)
     if s == "snapkv":
@@ -225,7 +236,7 @@ def cpu_leg(w: dict, budget_s: float, max_reps: int = 3):
     torch.set_num_threads(os.cpu_count() or 1)
     ratio = effective_ratio(w)
     # rough cost model (ms per 1k tokens on ~8 cores) to size the sample without trial runs
-    per_k = {"knorm": 3.5, "streaming": 3.0, "snapkv": 16.0, "expected_attention": 50.0}[w["scorer"]]
+    per_k = {"knorm": 3.5, "knorm_rerotate": 6.0, "streaming": 3.0, "snapkv": 16.0, "expected_attention": 50.0}[w["scorer"]]
     S = w["S"]
     while S > 4096 and per_k * S / 1000 / 1000 * max_reps > budget_s:
         S //= 2
@@ -360,8 +371,11 @@ def main():
     abytes = algorithmic_bytes(w, n_kept)
     achieved = abytes / (ms_per_step * 1e-3) / 1e9
     p = native.make_problem(sets[0][0], sets[0][1], n_kept, w["Hq"])
-    scorer_id = {"knorm": 1, "streaming": 2, "snapkv": 3, "expected_attention": 4}[w["scorer"]]
-    launches = native.launches_per_compress(p, scorer_id)
+    if w["scorer"] == "knorm_rerotate":  # kvp_knorm_score (1) + kvp_scores_compress_rerotate (generic: 3)
+        launches = 1 + native.launches_per_compress(p, 0)
+    else:
+        scorer_id = {"knorm": 1, "streaming": 2, "snapkv": 3, "expected_attention": 4}[w["scorer"]]
+        launches = native.launches_per_compress(p, scorer_id)
     roofline = {
         "bound": "hbm", "kernel": f"kvp_{w['scorer']}_compress ({launches} launches: score, select, compact)",
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],

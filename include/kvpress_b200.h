@@ -144,6 +144,15 @@ int kvp_scores_compress(const kvp_problem* p, const void* scores, const int64_t*
                         int32_t* idx_out, void* workspace, size_t workspace_bytes,
                         kvp_stream_t stream);
 
+/* ---- KeyRerotationPress (first "next" row): same selection as kvp_scores_compress, but each
+ * kept key is re-rotated from its original position s to its new position j (kvpress/presses/
+ * key_rerotation_press.py:50-152): k * cos((j-s) inv_freq) + rotate_half(k) * sin((j-s) inv_freq).
+ * inv_freq: fp32 [D/2] (module.rotary_emb.inv_freq); D must be a multiple of 16. Values are copied as is. */
+int kvp_scores_compress_rerotate(const kvp_problem* p, const void* scores, const int64_t* score_stride,
+                                 const void* K, const void* V, const float* inv_freq, void* K_out,
+                                 void* V_out, int32_t* idx_out, void* workspace,
+                                 size_t workspace_bytes, kvp_stream_t stream);
+
 /* ---- host-buffer convenience (end-to-end path): pageable or pinned HOST K/V in, HOST K'/V'
  * out; device staging buffers live in `workspace` (kvp_host_workspace_bytes). Copies are
  * enqueued on `stream`; the call returns after the stream has been synchronised. ---------- */

@@ -6,6 +6,7 @@ from kvpress_b200.pipeline import KVPressTextGenerationPipeline
 from kvpress_b200.presses.base_press import SUPPORTED_MODELS, BasePress
 from kvpress_b200.presses.decoding_press import DecodingPress
 from kvpress_b200.presses.expected_attention_press import ExpectedAttentionPress
+from kvpress_b200.presses.key_rerotation_press import KeyRerotationPress
 from kvpress_b200.presses.knorm_press import KnormPress
 from kvpress_b200.presses.scorer_press import ScorerPress
 from kvpress_b200.presses.snapkv_press import SnapKVPress
@@ -19,6 +20,7 @@ __all__ = [
     "ExpectedAttentionPress",
     "StreamingLLMPress",
     "DecodingPress",
+    "KeyRerotationPress",
     "KVPressTextGenerationPipeline",
     "SUPPORTED_MODELS",
 ]

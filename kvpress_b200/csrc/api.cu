@@ -352,6 +352,29 @@ int kvp_scores_compress(const kvp_problem* p, const void* scores, const int64_t*
     return select_and_compact(d, K, V, K_out, V_out, idx_out, ws, st);
 }
 
+int kvp_scores_compress_rerotate(const kvp_problem* p, const void* scores, const int64_t* score_stride,
+                                 const void* K, const void* V, const float* inv_freq, void* K_out,
+                                 void* V_out, int32_t* idx_out, void* workspace,
+                                 size_t workspace_bytes, kvp_stream_t stream) {
+    Dims d;
+    int rc = validate(p, &d);
+    if (rc) return rc;
+    if (d.D % 16 != 0) return KVP_ERR_UNSUPPORTED_SHAPE;  // rotate_half pairs d with d + D/2
+    if (d.n_kept == 0) return KVP_OK;
+    if ((rc = check_io(K, V, K_out, V_out))) return rc;
+    if (!scores || !score_stride || !inv_freq) return KVP_ERR_NULL_POINTER;
+    Workspace ws;
+    WsLayout L;
+    if ((rc = carve(d, KVP_SCORER_GENERIC, 0, workspace, workspace_bytes, &ws, &L))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(ws.hist_hi, 0, L.hist_bytes, st);
+    if (e != cudaSuccess) return fail_cuda(e);
+    e = launch_keys_from_scores(d, p->dtype, scores, score_stride[0], score_stride[1], ws, st);
+    if (e != cudaSuccess) return fail_cuda(e);
+    e = launch_select_compact_rerotate(d, p->dtype, K, V, K_out, V_out, idx_out, ws, inv_freq, st);
+    return e == cudaSuccess ? KVP_OK : fail_cuda(e);
+}
+
 // ---- host-buffer end-to-end path -------------------------------------------------------------------
 // workspace = [K_dev | V_dev | K_out_dev | V_out_dev | idx_dev | kernel scratch]
 static void host_layout(const Dims& d, size_t* k_off, size_t* v_off, size_t* ko_off,

@@ -233,6 +233,9 @@ cudaError_t launch_keys_from_scores(const Dims& d, int dtype, const void* scores
 cudaError_t launch_select_compact(const Dims& d, const void* K, const void* V, void* K_out,
                                   void* V_out, int32_t* idx_out, const Workspace& ws,
                                   cudaStream_t st);
+cudaError_t launch_select_compact_rerotate(const Dims& d, int dtype, const void* K, const void* V,
+                                           void* K_out, void* V_out, int32_t* idx_out,
+                                           const Workspace& ws, const float* inv_freq, cudaStream_t st);
 cudaError_t launch_streaming_score(const Dims& d, int dtype, int n_sink, void* scores_out,
                                    cudaStream_t st);
 cudaError_t launch_streaming_compress(const Dims& d, int n_sink, const void* K, const void* V,

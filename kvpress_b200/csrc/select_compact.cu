@@ -15,6 +15,8 @@
 //                    position order. Ties at T go to the lowest positions.
 // Tiles are visited in REVERSE order of the score stage so the K rows touched last (still in the
 // 126 MB L2) are re-read first.
+#include <type_traits>
+
 #include "common.cuh"
 #include "knorm_chunk.cuh"
 
@@ -102,6 +104,67 @@ __device__ __forceinline__ void copy_rows_kv(const char* __restrict__ srcK, int6
             load(ak, av, base);
             store(ak, av, base);
         }
+    }
+}
+
+// KeyRerotationPress epilogue (reference kvpress/presses/key_rerotation_press.py:50-131): the kept key
+// that lands at output position j came from position s; it is rotated by delta = j - s positions:
+//     out = k * cos(delta * inv_freq) + rotate_half(k) * sin(delta * inv_freq)
+// with the reference's rounding points: angle and cos/sin in fp32, cos/sin rounded to the cache dtype, each
+// product and the sum rounded to the cache dtype. A thread handles the vector pair (d, d + D/2).
+template <typename T>
+__device__ __forceinline__ void copy_rows_k_rerotated(const char* __restrict__ srcK, int64_t k_row_bytes,
+                                                      char* __restrict__ dstK, int64_t dst_row_bytes,
+                                                      const int* __restrict__ list, int count, int D,
+                                                      const float* __restrict__ inv_freq, int out_pos0) {
+    const int half_vec = D >> 4;  // 16-byte vectors in half a row
+    const int total = count * half_vec;
+    const uint64_t pol_first = l2_policy_evict_first();
+    for (int i = threadIdx.x; i < total; i += kTileThreads) {
+        const int r = i / half_vec, cc = i - r * half_vec;
+        const int s = list[r];
+        const float delta = (float)(out_pos0 + r) - (float)s;
+        const char* src = srcK + (int64_t)s * k_row_bytes;
+        const int4 lo = ldg_plain(src + cc * 16);
+        const int4 hi = ldg_plain(src + (cc + half_vec) * 16);
+        const uint32_t wl[4] = {(uint32_t)lo.x, (uint32_t)lo.y, (uint32_t)lo.z, (uint32_t)lo.w};
+        const uint32_t wh[4] = {(uint32_t)hi.x, (uint32_t)hi.y, (uint32_t)hi.z, (uint32_t)hi.w};
+        uint32_t ol[4], oh[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint16_t rl[2], rh[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float f = delta * __ldg(inv_freq + cc * 8 + w * 2 + e);
+                float sn, cs;
+                sincosf(f, &sn, &cs);
+                const float c16 = F16Traits<T>::to_float(F16Traits<T>::from_float(cs));
+                const float s16 = F16Traits<T>::to_float(F16Traits<T>::from_float(sn));
+                const float kl = F16Traits<T>::to_float((uint16_t)(wl[w] >> (16 * e)));
+                const float kh = F16Traits<T>::to_float((uint16_t)(wh[w] >> (16 * e)));
+                auto rn = [](float x) { return F16Traits<T>::to_float(F16Traits<T>::from_float(x)); };
+                rl[e] = F16Traits<T>::from_float(rn(kl * c16) + rn(-kh * s16));
+                rh[e] = F16Traits<T>::from_float(rn(kh * c16) + rn(kl * s16));
+            }
+            ol[w] = (uint32_t)rl[0] | ((uint32_t)rl[1] << 16);
+            oh[w] = (uint32_t)rh[0] | ((uint32_t)rh[1] << 16);
+        }
+        char* dst = dstK + (int64_t)r * dst_row_bytes;
+        stg_hint(dst + cc * 16, make_int4((int)ol[0], (int)ol[1], (int)ol[2], (int)ol[3]), pol_first);
+        stg_hint(dst + (cc + half_vec) * 16, make_int4((int)oh[0], (int)oh[1], (int)oh[2], (int)oh[3]), pol_first);
+    }
+}
+
+// Plain copy of one tensor's rows (the V half of a rerotating compaction).
+__device__ __forceinline__ void copy_rows_single(const char* __restrict__ src, int64_t row_bytes_src,
+                                                 char* __restrict__ dst, int64_t dst_row_bytes,
+                                                 const int* __restrict__ list, int count, int nvec) {
+    const int total = count * nvec;
+    const uint64_t pol_first = l2_policy_evict_first();
+    for (int i = threadIdx.x; i < total; i += kTileThreads) {
+        const int r = i / nvec, cc = i - r * nvec;
+        const int4 v = ldg_hint(src + (int64_t)list[r] * row_bytes_src + cc * 16, pol_first);
+        stg_hint(dst + (int64_t)r * dst_row_bytes + cc * 16, v, pol_first);
     }
 }
 
@@ -286,10 +349,12 @@ __device__ __forceinline__ void refine_item(SelectSmem& sm, int row, int group, 
 }
 
 // ---- compact item: (row, tile of kTile == kTileThreads positions, one per thread) ---------------------
+template <typename TR = void>  // TR = void: plain copy; TR = cache dtype: KeyRerotationPress epilogue
 __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, const char* K,
                                              const char* V, Strides3 ks, Strides3 vs, char* K_out,
                                              char* V_out, int32_t* idx_out, int H, int S, int D,
-                                             int n_kept, const Workspace& ws) {
+                                             int n_kept, const Workspace& ws,
+                                             const float* inv_freq = nullptr) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = row / H, h = row % H;
     const int s = tile * kTile + tid;
@@ -353,10 +418,16 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
         const int64_t out_row0 = (int64_t)row * n_kept + out_base;
         if (idx_out != nullptr && tid < count) idx_out[out_row0 + tid] = sm.list[tid];
         const int64_t row_bytes = (int64_t)D * 2;
-        copy_rows_kv<KVP_SEL_U, KVP_SEL_TWO>(K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2, ks.s * 2,
-                     V + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2, vs.s * 2,
-                     K_out + out_row0 * row_bytes, V_out + out_row0 * row_bytes, row_bytes, sm.list,
-                     count, D >> 3);
+        const char* k_src = K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2;
+        const char* v_src = V + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2;
+        if constexpr (std::is_void<TR>::value) {
+            copy_rows_kv<KVP_SEL_U, KVP_SEL_TWO>(k_src, ks.s * 2, v_src, vs.s * 2, K_out + out_row0 * row_bytes,
+                                                 V_out + out_row0 * row_bytes, row_bytes, sm.list, count, D >> 3);
+        } else {
+            copy_rows_k_rerotated<TR>(k_src, ks.s * 2, K_out + out_row0 * row_bytes, row_bytes, sm.list, count, D,
+                                      inv_freq, (int)out_base);
+            copy_rows_single(v_src, vs.s * 2, V_out + out_row0 * row_bytes, row_bytes, sm.list, count, D >> 3);
+        }
     }
     SEL_ACC(2, t_copy);
     SEL_CNT(3);
@@ -367,11 +438,12 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
 // flag), items [nA, nA + nB) the compact items (last rows / last tiles first, so K rows the score
 // stage touched last are re-read while still in L2). A compact item only waits for refine items,
 // which precede it in the queue and never wait themselves => no deadlock for any grid size.
+template <typename TR>
 __global__ void __launch_bounds__(kTileThreads, KVP_SEL_CTAS)
 select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, Strides3 ks,
                       Strides3 vs, char* __restrict__ K_out, char* __restrict__ V_out,
                       int32_t* __restrict__ idx_out, int H, int S, int D, int n_kept,
-                      Workspace ws) {
+                      Workspace ws, const float* __restrict__ inv_freq) {
     __shared__ SelectSmem sm;
     const int R = ws.R;
     const int n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
@@ -394,7 +466,7 @@ select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, St
             const int j = item - nA;
             const int row = R - 1 - j / ws.n_tiles;
             const int tile = ws.n_tiles - 1 - j % ws.n_tiles;
-            compact_item(sm, row, tile, K, V, ks, vs, K_out, V_out, idx_out, H, S, D, n_kept, ws);
+            compact_item<TR>(sm, row, tile, K, V, ks, vs, K_out, V_out, idx_out, H, S, D, n_kept, ws, inv_freq);
         }
     }
     SEL_ACC(7, t_kernel);
@@ -415,17 +487,33 @@ static int persistent_grid(const void* kernel, int threads, int n_items) {
     return n_items < grid ? n_items : grid;
 }
 
+template <typename TR>
+static cudaError_t launch_select_compact_t(const Dims& d, const void* K, const void* V, void* K_out,
+                                           void* V_out, int32_t* idx_out, const Workspace& ws,
+                                           const float* inv_freq, cudaStream_t st) {
+    const int n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
+    const int n_items = d.R * n_groups + d.R * ws.n_tiles;
+    auto kern = select_compact_kernel<TR>;
+    const int grid = persistent_grid(reinterpret_cast<const void*>(kern), kTileThreads, n_items);
+    kern<<<grid, kTileThreads, 0, st>>>(static_cast<const char*>(K), static_cast<const char*>(V), d.ks, d.vs,
+                                        static_cast<char*>(K_out), static_cast<char*>(V_out), idx_out, d.H,
+                                        d.S, d.D, d.n_kept, ws, inv_freq);
+    return cudaPeekAtLastError();
+}
+
 cudaError_t launch_select_compact(const Dims& d, const void* K, const void* V, void* K_out,
                                   void* V_out, int32_t* idx_out, const Workspace& ws,
                                   cudaStream_t st) {
-    const int n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
-    const int n_items = d.R * n_groups + d.R * ws.n_tiles;
-    const int grid =
-        persistent_grid(reinterpret_cast<const void*>(select_compact_kernel), kTileThreads, n_items);
-    select_compact_kernel<<<grid, kTileThreads, 0, st>>>(
-        static_cast<const char*>(K), static_cast<const char*>(V), d.ks, d.vs,
-        static_cast<char*>(K_out), static_cast<char*>(V_out), idx_out, d.H, d.S, d.D, d.n_kept, ws);
-    return cudaPeekAtLastError();
+    return launch_select_compact_t<void>(d, K, V, K_out, V_out, idx_out, ws, nullptr, st);
+}
+
+// Same selection, keys re-rotated to their new positions (KeyRerotationPress); inv_freq: fp32 [D/2].
+cudaError_t launch_select_compact_rerotate(const Dims& d, int dtype, const void* K, const void* V,
+                                           void* K_out, void* V_out, int32_t* idx_out,
+                                           const Workspace& ws, const float* inv_freq, cudaStream_t st) {
+    if (dtype == KVP_BF16)
+        return launch_select_compact_t<__nv_bfloat16>(d, K, V, K_out, V_out, idx_out, ws, inv_freq, st);
+    return launch_select_compact_t<__half>(d, K, V, K_out, V_out, idx_out, ws, inv_freq, st);
 }
 
 // ---- KnormPress: score + select + compact in ONE persistent kernel ---------------------------------

@@ -65,6 +65,8 @@ SIGNATURES = {
         ctypes.c_int, [_PP, _P, _P, _P, _P, ctypes.c_float, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "kvp_scores_compress": (
         ctypes.c_int, [_PP, _P, ctypes.POINTER(ctypes.c_int64), _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "kvp_scores_compress_rerotate": (
+        ctypes.c_int, [_PP, _P, ctypes.POINTER(ctypes.c_int64), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "kvp_host_workspace_bytes": (ctypes.c_int, [_PP, ctypes.c_int, ctypes.POINTER(_SZ)]),
     "kvp_knorm_compress_host": (ctypes.c_int, [_PP, _P, _P, _P, _P, _P, _P, _SZ, _P]),
 }
@@ -364,6 +366,35 @@ def scores_compress(scores: torch.Tensor, keys, values, n_kept: int, return_indi
                     ctypes.byref(p), _ptr(scores), sstride, _ptr(keys), _ptr(values), _ptr(k_out), _ptr(v_out),
                     _ptr(idx), _ptr(ws), ws.numel(), _stream()),
                 "kvp_scores_compress",
+            )
+    return k_out, v_out, idx
+
+
+def scores_compress_rerotate(scores: torch.Tensor, keys, values, n_kept: int, inv_freq: torch.Tensor,
+                             return_indices: bool = False):
+    """KeyRerotationPress: top-k + compaction with the kept keys re-rotated to their new positions."""
+    _require_cuda_kv(keys, values)
+    keys, values = _normalise(keys), _normalise(values)
+    if tuple(scores.shape) != tuple(keys.shape[:3]) or scores.device != keys.device:
+        raise RuntimeError(f"scores must be [B, Hkv, S] on the cache device, got {tuple(scores.shape)}")
+    if inv_freq.numel() * 2 != keys.shape[3]:
+        raise RuntimeError(f"inv_freq must have head_dim/2 = {keys.shape[3] // 2} entries, got {inv_freq.numel()}")
+    scores = scores.to(keys.dtype)
+    if scores.stride(2) != 1:
+        scores = scores.contiguous()
+    inv_freq = inv_freq.to(device=keys.device, dtype=torch.float32).contiguous()
+    p = make_problem(keys, values, n_kept)
+    k_out, v_out, idx, _ = _alloc_out(keys, n_kept, return_indices, False)
+    if n_kept > 0:
+        sstride = (ctypes.c_int64 * 2)(
+            scores.stride(0) if scores.shape[0] > 1 else 0, scores.stride(1) if scores.shape[1] > 1 else 0)
+        with torch.cuda.device(keys.device):
+            ws = _workspace(p, SCORER_GENERIC, keys.device)
+            _check(
+                load().kvp_scores_compress_rerotate(
+                    ctypes.byref(p), _ptr(scores), sstride, _ptr(keys), _ptr(values), _ptr(inv_freq), _ptr(k_out),
+                    _ptr(v_out), _ptr(idx), _ptr(ws), ws.numel(), _stream()),
+                "kvp_scores_compress_rerotate",
             )
     return k_out, v_out, idx
 

@@ -252,6 +252,34 @@ def expected_attention_scores_fp32(keys, values, mu, cov, epsilon: float, n_sink
 
 
 # --------------------------------------------------------------------------------------------------
+# key_rerotation_press.py:50-152 (SURVEY §8f "next" row 1)
+# --------------------------------------------------------------------------------------------------
+def rerotate_cos_sin(dtype, inv_freq: torch.Tensor, selected_positions: torch.Tensor):
+    """key_rerotation_press.py:50-94 — cos/sin of (new position - old position) * inv_freq, computed in
+    fp32 and rounded to the key dtype. selected_positions [B,H,n_kept] ascending; inv_freq [D/2]."""
+    B, H, n_kept = selected_positions.shape
+    idx = torch.arange(0, n_kept).float()[None, None, :].expand(B, H, n_kept)
+    delta = (idx - selected_positions).unsqueeze(2)                        # [B,H,1,n_kept]
+    freqs = (delta.float() * inv_freq[None, None, :, None].float()).transpose(2, 3)  # [B,H,n_kept,D/2]
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos().contiguous().to(dtype), emb.sin().contiguous().to(dtype)
+
+
+def rerotate_keys(keys: torch.Tensor, indices: torch.Tensor, inv_freq: torch.Tensor) -> torch.Tensor:
+    """key_rerotation_press.py:96-131 — gather the kept keys (indices ascending) and rotate each from its
+    old position to its new one. Products and the sum round to the key dtype (plain ATen ops)."""
+    cos, sin = rerotate_cos_sin(keys.dtype, inv_freq, indices)
+    k = gather_rows(keys, indices)
+    return (k * cos) + (rotate_half(k) * sin)
+
+
+def key_rerotation_compress(scores, keys, values, n_kept: int, inv_freq):
+    """key_rerotation_press.py:133-152 with the scores given. Returns (K'', V', ascending indices)."""
+    idx = torch.sort(topk_indices(scores, n_kept), dim=2).values
+    return rerotate_keys(keys, idx, inv_freq), gather_rows(values, idx), idx
+
+
+# --------------------------------------------------------------------------------------------------
 # decoding_press.py:194-236
 # --------------------------------------------------------------------------------------------------
 def find_target_compression_ratio(q_len: int, target_tokens: int) -> float:

@@ -61,8 +61,14 @@ def scores_compress(scores, keys, values, n_kept, return_indices=False):
     return k_out, v_out, idx
 
 
+def scores_compress_rerotate(scores, keys, values, n_kept, inv_freq, return_indices=False):
+    idx = O.select_lowest_index_ties(scores, n_kept)
+    k_out = O.rerotate_keys(keys, idx, inv_freq.float())
+    return k_out, O.gather_rows(values, idx), (idx.to(torch.int32) if return_indices else None)
+
+
 PATCHED = ["knorm_score", "knorm_compress", "streaming_score", "streaming_compress", "snapkv_score",
-           "snapkv_compress", "expected_attention_score", "expected_attention_compress", "scores_compress"]
+           "snapkv_compress", "expected_attention_score", "expected_attention_compress", "scores_compress", "scores_compress_rerotate"]
 
 
 def install(monkeypatch):

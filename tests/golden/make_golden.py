@@ -127,9 +127,62 @@ def make_decoding_table():
     print("decoding table", rows[:3])
 
 
+def make_rerotation():
+    """key_rerotation_press.py:133-152 run unmodified. Two wrapped scorers per case: the
+    reference KnormPress (realistic, ties in bf16) and a ScorerPress subclass whose scores are a seeded
+    permutation of DISTINCT 16-bit values, so the kept set is unambiguous and outputs compare row by row."""
+    kvpress = import_reference()
+    from dataclasses import dataclass
+    from types import SimpleNamespace
+
+    @dataclass
+    class PermutationPress(kvpress.ScorerPress):
+        scores: torch.Tensor = None
+
+        def score(self, module, hidden_states, keys, values, attentions, kwargs):
+            return self.scores
+
+    out = {}
+    cases = [("a", 2, 2, 384, 64, torch.bfloat16, 10000.0), ("b", 1, 2, 700, 128, torch.bfloat16, 500000.0),
+             ("c", 1, 2, 300, 64, torch.float16, 10000.0)]
+    out["cases"] = np.array([[B, H, S, D, int(dt == torch.float16)] for _, B, H, S, D, dt, _ in cases], dtype=np.int64)
+    out["ratios"] = np.array([0.25, 0.5, 0.8])
+    for tag, B, H, S, D, dtype, theta in cases:
+        torch.manual_seed(100 + S)
+        keys, values = torch.randn(B, H, S, D).to(dtype), torch.randn(B, H, S, D).to(dtype)
+        inv_freq = 1.0 / (theta ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))
+        module = SimpleNamespace(rotary_emb=SimpleNamespace(inv_freq=inv_freq), head_dim=D)
+        perm = torch.stack([torch.randperm(S) for _ in range(B * H)]).view(B, H, S)
+        scores = (perm + 0x3000).to(torch.int16).view(dtype)  # distinct positive finite values
+        assert scores.float().flatten(0, 1).unique(dim=-1).shape[-1] == S
+        out[f"{tag}_keys"], out[f"{tag}_values"] = u16(keys), u16(values)
+        out[f"{tag}_inv_freq"], out[f"{tag}_scores"] = inv_freq.numpy(), u16(scores)
+        for i, r in enumerate(out["ratios"]):
+            r = float(r)
+            with torch.no_grad():
+                press = kvpress.KeyRerotationPress(PermutationPress(compression_ratio=r, scores=scores))
+                k2, v2 = press.compress(module, None, keys, values, None, {})
+                out[f"{tag}_perm_k_{i}"] = u16(k2)
+                if i == 0:
+                    out[f"{tag}_perm_v_{i}"] = u16(v2)
+                kn = kvpress.KnormPress(compression_ratio=r)
+                sc = kn.score(module, None, keys, values, None, {})
+                idx = sc.topk(int(S * (1 - r)), dim=-1).indices.sort(dim=2).values
+                k3, v3 = kvpress.KeyRerotationPress(kn).compress(module, None, keys, values, None, {})
+                out[f"{tag}_knorm_idx_{i}"] = idx.numpy().astype(np.int32)
+                assert torch.equal(v3, values.gather(2, idx.unsqueeze(-1).expand(-1, -1, -1, D)))
+                out[f"{tag}_knorm_k_{i}"] = u16(k3)
+    np.savez_compressed(OUT / "rerotation.npz", **out)
+    print("rerotation", out["cases"].tolist())
+
+
 if __name__ == "__main__":
+    if "--rerotation-only" in sys.argv:
+        make_rerotation()
+        sys.exit(0)
     make_case("small64", B=2, Hq=4, Hkv=2, D=64, hidden=256, S=384, seed=11)
     make_case("llama128", B=1, Hq=8, Hkv=2, D=128, hidden=512, S=1200, seed=12)
     make_case("ties128", B=1, Hq=4, Hkv=1, D=128, hidden=256, S=2500, seed=13, heavy_tail=True)
     make_case("half64", B=1, Hq=2, Hkv=2, D=64, hidden=128, S=300, seed=14, dtype=torch.float16)
     make_decoding_table()
+    make_rerotation()

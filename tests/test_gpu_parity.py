@@ -442,3 +442,92 @@ def test_expected_attention_eight_heads_per_kv_head():
     hi = O.expected_attention_scores_fp32(k, v, mu, cov, 0.0, 4, True)
     ref = O.expected_attention_scores(k, v, mu, cov, 0.0, 4, True)
     _assert_scores_close(got, ref, hi, slice(0, 4), torch.bfloat16)
+
+
+# ---------------------------------------------------------------------------------------------------
+# KeyRerotationPress: selection + compaction with the K rows re-rotated
+# ---------------------------------------------------------------------------------------------------
+def _assert_rerotated_close(got: torch.Tensor, ref: torch.Tensor, src_rows: torch.Tensor):
+    """cos/sin come from CUDA's sincosf here and from the host libm in the reference run: an fp32 last-bit
+    difference can flip the 16-bit rounding of cos or sin, which moves a product by one 16-bit ulp. So:
+    nearly all elements bit-exact, the rest within 2^-6 of the row's largest |k| (2 ulp at that scale)."""
+    got, ref = got.cpu(), ref.cpu()
+    exact = (got.view(torch.int16) == ref.view(torch.int16)).float().mean().item()
+    assert exact > 0.995, exact
+    bound = src_rows.cpu().float().abs().amax(-1, keepdim=True) * 2.0 ** -6
+    assert ((got.float() - ref.float()).abs() <= bound).all()
+
+
+def test_key_rerotation_vs_golden():
+    import numpy as np
+
+    from tests.conftest import GOLDEN_DIR
+    nat = _native()
+    z = np.load(GOLDEN_DIR / "rerotation.npz")
+    for tag, (B, H, S, D, is_half) in zip("abc", z["cases"]):
+        dtype = torch.float16 if is_half else torch.bfloat16
+        t16 = lambda k: torch.from_numpy(z[f"{tag}_{k}"].copy()).view(dtype)  # noqa: E731
+        keys, values, scores = t16("keys").to(DEV), t16("values").to(DEV), t16("scores").to(DEV)
+        inv_freq = torch.from_numpy(z[f"{tag}_inv_freq"].copy()).to(DEV)
+        for i, r in enumerate(z["ratios"]):
+            n_kept = O.kept_count(int(S), float(r))
+            k2, v2, idx = nat.scores_compress_rerotate(scores, keys, values, n_kept, inv_freq, return_indices=True)
+            ref_idx = O.select_lowest_index_ties(scores.cpu(), n_kept)
+            assert torch.equal(idx.long().cpu(), ref_idx)
+            assert torch.equal(v2.cpu(), O.gather_rows(values.cpu(), ref_idx))
+            _assert_rerotated_close(k2, t16(f"perm_k_{i}"), O.gather_rows(keys.cpu(), ref_idx))
+            # the Knorm-wrapped golden: same kept set whenever the reference's top-k had no threshold tie
+            kn_idx = torch.from_numpy(z[f"{tag}_knorm_idx_{i}"].copy()).long()
+            kn_scores = nat.knorm_score(keys)
+            k3, _, idx3 = nat.scores_compress_rerotate(kn_scores, keys, values, n_kept, inv_freq, return_indices=True)
+            O.check_selection(kn_scores.cpu(), idx3.long().cpu(), n_kept)
+            if torch.equal(idx3.long().cpu(), kn_idx):
+                _assert_rerotated_close(k3, t16(f"knorm_k_{i}"), O.gather_rows(keys.cpu(), kn_idx))
+
+
+@pytest.mark.parametrize("shape,theta", [((1, 4, 8192, 128), 500000.0), ((2, 2, 3001, 64), 10000.0),
+                                         ((1, 8, 40000, 128), 10000.0), ((1, 2, 777, 256), 1e6)])
+@pytest.mark.parametrize("ratio", [0.3, 0.9])
+def test_key_rerotation_vs_oracle_random(shape, theta, ratio):
+    nat = _native()
+    B, H, S, D = shape
+    g = torch.Generator().manual_seed(S + D)
+    keys, values = (torch.randn(shape, generator=g).to(torch.bfloat16).to(DEV) for _ in range(2))
+    scores = torch.randn(B, H, S, generator=g).to(torch.bfloat16).to(DEV)
+    inv_freq = 1.0 / (theta ** (torch.arange(0, D, 2).float() / D))
+    n_kept = O.kept_count(S, ratio)
+    k2, v2, idx = nat.scores_compress_rerotate(scores, keys, values, n_kept, inv_freq.to(DEV), return_indices=True)
+    ref_idx = O.select_lowest_index_ties(scores.cpu(), n_kept)
+    assert torch.equal(idx.long().cpu(), ref_idx)
+    ref_k, ref_v, _ = O.rerotate_keys(keys.cpu(), ref_idx, inv_freq), O.gather_rows(values.cpu(), ref_idx), None
+    assert torch.equal(v2.cpu(), ref_v)
+    _assert_rerotated_close(k2, ref_k, O.gather_rows(keys.cpu(), ref_idx))
+
+
+def test_key_rerotation_full_size_properties():
+    """Llama-8B 128k layer. (1) inv_freq = 0 is the identity rotation: bit-identical to kvp_scores_compress.
+    (2) a rotation preserves the norm of every (d, d + D/2) pair up to the 16-bit roundings. (3) rotating the
+    compacted keys back by the opposite angle recovers the gathered rows (same tolerance)."""
+    nat = _native()
+    B, H, S, D = 1, 8, 131072, 128
+    g = torch.Generator(device=DEV).manual_seed(3)
+    keys = torch.randn(B, H, S, D, generator=g, device=DEV, dtype=torch.float32).to(torch.bfloat16)
+    values = torch.randn(B, H, S, D, generator=g, device=DEV, dtype=torch.float32).to(torch.bfloat16)
+    scores = torch.randn(B, H, S, generator=g, device=DEV, dtype=torch.float32).to(torch.bfloat16)
+    n_kept = O.kept_count(S, 0.7)
+    k0, v0, i0 = nat.scores_compress(scores, keys, values, n_kept, return_indices=True)
+    k1, v1, i1 = nat.scores_compress_rerotate(scores, keys, values, n_kept, torch.zeros(D // 2, device=DEV),
+                                              return_indices=True)
+    assert torch.equal(i0, i1) and torch.equal(v0, v1) and torch.equal(k0, k1)
+    inv_freq = (1.0 / (500000.0 ** (torch.arange(0, D, 2).float() / D))).to(DEV)
+    k2, v2, i2 = nat.scores_compress_rerotate(scores, keys, values, n_kept, inv_freq, return_indices=True)
+    assert torch.equal(i0, i2) and torch.equal(v0, v2)
+    pair = lambda x: torch.hypot(x[..., : D // 2].float(), x[..., D // 2:].float())  # noqa: E731
+    assert torch.allclose(pair(k2), pair(k0), rtol=0, atol=2.0 ** -6 * 6)
+    delta = (torch.arange(n_kept, device=DEV)[None, None, :] - i0.long()).float()       # new - old position
+    ang = delta[..., None] * inv_freq
+    c, s = torch.cos(ang), torch.sin(ang)
+    lo, hi = k2[..., : D // 2].float(), k2[..., D // 2:].float()
+    back = torch.cat((lo * c + hi * s, hi * c - lo * s), dim=-1)                          # rotate by -angle
+    assert (back - k0.float()).abs().max().item() < 0.08
+    assert (back - k0.float()).abs().mean().item() < 0.006

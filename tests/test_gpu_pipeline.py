@@ -145,3 +145,34 @@ def test_decoding_press_on_gpu(qwen, base):
     pipe(words(400, seed=5), question=words(6, seed=6), press=press, max_new_tokens=80)
     assert len(sizes) >= 40
     assert min(sizes[16:]) >= 256 and max(sizes[16:]) <= 256 + 16 - 1 and 256 in sizes
+
+
+@pytest.mark.parametrize("inner", [KnormPress(0.5), SnapKVPress(0.4), StreamingLLMPress(0.6)])
+def test_key_rerotation_press_through_hook_vs_oracle(model, inner, monkeypatch):
+    """KeyRerotationPress around a scorer press, through the forward hook on a bf16 model: V rows are cache rows,
+    K rows are the oracle's re-rotation of the kept cache rows."""
+    from kvpress_b200 import KeyRerotationPress, native
+
+    kept, real = [], native.scores_compress_rerotate
+
+    def spy(scores, keys, values, n_kept, inv_freq, return_indices=False):
+        k, v, idx = real(scores, keys, values, n_kept, inv_freq, return_indices=True)
+        kept.append(idx.long().cpu())
+        return k, v, idx
+
+    monkeypatch.setattr(native, "scores_compress_rerotate", spy)
+    ids = torch.randint(2, 250, (2, 700), device=DEV)
+    full = _full_cache(model, ids)
+    cache = DynamicCache()
+    with KeyRerotationPress(inner)(model):
+        model.model(input_ids=ids, past_key_values=cache)
+    n_kept = kept_count(700, inner.compression_ratio)
+    assert cache.get_seq_length() == n_kept and len(kept) == len(cache.layers)
+    inv_freq = model.model.rotary_emb.inv_freq.float().cpu()
+    for lf, lc, pos in zip(full.layers, cache.layers, kept):
+        assert (pos[..., 1:] > pos[..., :-1]).all()
+        assert torch.equal(O.gather_rows(lf.values.cpu(), pos), lc.values.cpu())
+        ref_k = O.rerotate_keys(lf.keys.cpu(), pos, inv_freq)
+        exact = (ref_k.view(torch.int16) == lc.keys.cpu().view(torch.int16)).float().mean().item()
+        assert exact > 0.99, exact
+        assert (ref_k.float() - lc.keys.cpu().float()).abs().max().item() <= 2.0 ** -6 * lf.keys.float().abs().max().item()

@@ -103,3 +103,31 @@ def test_ulp_helper():
     a = torch.tensor([1.0, -1.0, 0.0], dtype=torch.bfloat16)
     b = torch.tensor([1.0078125, -1.0078125, -0.0], dtype=torch.bfloat16)
     assert ulp16_diff(a, b).tolist() == [1, 1, 0]
+
+
+# ---- KeyRerotationPress ------------------------------------------------------------
+def _rerotation_cases():
+    z = np.load(GOLDEN_DIR / "rerotation.npz")
+    for tag, (B, H, S, D, is_half) in zip("abc", z["cases"]):
+        dtype = torch.float16 if is_half else torch.bfloat16
+        get = lambda k, tag=tag, dtype=dtype: (  # noqa: E731
+            torch.from_numpy(z[f"{tag}_{k}"].copy()).view(dtype) if z[f"{tag}_{k}"].dtype == np.uint16
+            else torch.from_numpy(z[f"{tag}_{k}"].copy()))
+        yield tag, int(S), [float(r) for r in z["ratios"]], get
+
+
+def test_rerotation_matches_reference_bit_exact():
+    """The oracle's rerotate_keys / key_rerotation_compress against KeyRerotationPress.compress outputs."""
+    for tag, S, ratios, get in _rerotation_cases():
+        keys, values, inv_freq, scores = get("keys"), get("values"), get("inv_freq"), get("scores")
+        for i, r in enumerate(ratios):
+            n_kept = O.kept_count(S, r)
+            k2, v2, idx = O.key_rerotation_compress(scores, keys, values, n_kept, inv_freq)
+            assert torch.equal(k2.view(torch.int16), get(f"perm_k_{i}").view(torch.int16)), (tag, r)
+            if i == 0:
+                assert torch.equal(v2, get("perm_v_0"))
+            # canonical (lowest-index ties) selection coincides when scores are distinct
+            assert torch.equal(O.select_lowest_index_ties(scores, n_kept), idx)
+            kn_idx = get(f"knorm_idx_{i}").long()
+            k3 = O.rerotate_keys(keys, kn_idx, inv_freq)
+            assert torch.equal(k3.view(torch.int16), get(f"knorm_k_{i}").view(torch.int16)), (tag, r)

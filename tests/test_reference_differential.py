@@ -73,3 +73,32 @@ def test_same_rows_as_reference(monkeypatch, ref, name, ref_cls, our_cls, kw, ra
         else:
             assert torch.allclose(_rows_signature(lo.keys, lo.values), _rows_signature(lt.keys, lt.values),
                                   atol=1e-9)
+
+
+@pytest.mark.parametrize("inner", ["streaming", "snapkv"])
+@pytest.mark.parametrize("family", ["llama", "qwen3"])
+def test_key_rerotation_same_cache_as_reference(monkeypatch, ref, inner, family):
+    """KeyRerotationPress (key_rerotation_press.py:133-152): the reference sorts the kept indices, so the
+    compacted cache must agree ROW BY ROW, re-rotated keys included."""
+    from kvpress_b200 import KeyRerotationPress
+
+    cpu_backend.install(monkeypatch)
+    model = tiny_llama() if family == "llama" else tiny_qwen3()
+    g = torch.Generator().manual_seed(7)
+    ids = torch.stack([torch.randperm(250, generator=g)[:160] + 2 for _ in range(2)])
+    S, ratio = ids.shape[1], 0.4
+    _, ref_cls, our_cls, kw = next(c for c in CASES if c[0] == inner)
+
+    theirs = DynamicCache()
+    with ref.KeyRerotationPress(ref_cls(ref)(compression_ratio=ratio, **kw))(model):
+        model.model(input_ids=ids, past_key_values=theirs, cache_position=torch.arange(S))
+    ours = DynamicCache()
+    press = KeyRerotationPress(our_cls(compression_ratio=ratio, **kw))
+    assert press.compression_ratio == ratio
+    with press(model):
+        model.model(input_ids=ids, past_key_values=ours)
+
+    assert ours.get_seq_length() == theirs.get_seq_length() == int(S * (1 - ratio))
+    for lo, lt in zip(ours.layers, theirs.layers):
+        assert torch.equal(lo.values, lt.values)
+        assert torch.equal(lo.keys, lt.keys)
