@@ -286,6 +286,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("KVP_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=list(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-mode", default="auto", choices=["auto", "serial", "staged", "zero_copy"],
+                    help="host path: serial = H2D, compress, D2H on one stream; staged = per-kv-head 3-stream pipeline "
+                         "(kvpress_b200.host_staging); zero_copy = staged + kept V rows read in place over PCIe")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
 
@@ -400,12 +403,33 @@ def main():
         out_v = torch.empty_like(out_k).pin_memory()
         e2e_steps = max(2, min(args.steps, 8))
 
+        from kvpress_b200 import host_staging
+
+        mode = args.e2e_mode
+        if mode == "auto":
+            # measured (profiles/r01_e2e_modes.txt): zero_copy > staged > serial wherever V is not read to score
+            mode = {"knorm_rerotate": "serial", "expected_attention": "staged"}.get(w["scorer"], "zero_copy")
+        if mode == "zero_copy" and w["scorer"] in ("expected_attention", "knorm_rerotate"):
+            raise SystemExit("zero_copy needs a scorer that does not read V to score")
+
+        extra_pinned = {k: v.cpu().pin_memory() for k, v in extra_h.items()}  # small operands travel every step too
+
         def e2e_step():
-            Kd = Kh.to(device, non_blocking=True)
-            Vd = Vh.to(device, non_blocking=True)
-            k2, v2 = run_native(w, Kd, Vd, extra_h, n_kept)
-            out_k.copy_(k2, non_blocking=True)
-            out_v.copy_(v2, non_blocking=True)
+            extra_d = {k: v.to(device, non_blocking=True) for k, v in extra_pinned.items()}
+            if mode == "serial":
+                Kd = Kh.to(device, non_blocking=True)
+                Vd = Vh.to(device, non_blocking=True)
+                k2, v2 = run_native(w, Kd, Vd, extra_d, n_kept)
+                out_k.copy_(k2, non_blocking=True)
+                out_v.copy_(v2, non_blocking=True)
+                return
+            params = dict(extra_d)
+            if w["scorer"] == "snapkv":
+                params.update(window=64, kernel_size=5)
+            if w["scorer"] == "expected_attention":
+                params.update(epsilon=0.0, n_sink=4, use_vnorm=True)
+            host_staging.compress_host(w["scorer"], Kh, Vh, n_kept, device=device, out_keys=out_k, out_values=out_v,
+                                       heads_per_chunk=1, values_zero_copy=(mode == "zero_copy"), **params)
 
         for _ in range(3):
             e2e_step()
@@ -417,10 +441,19 @@ def main():
         torch.cuda.synchronize()
         barrier()
         e2e_ms = max_over_ranks(start.elapsed_time(stop), dist, device) / e2e_steps
+        small = sum(v.numel() * v.element_size() for v in extra_pinned.values())
+        h2d_bytes = small + {"serial": 2 * Kh.numel() * 2, "staged": 2 * Kh.numel() * 2,
+                             "zero_copy": (2 * out_k.numel() * 2 if w["scorer"] == "streaming"
+                                           else Kh.numel() * 2 + out_v.numel() * 2)}[mode]
         e2e = {
             "value": tokens_per_step / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
-            "h2d_bytes_per_step": 2 * Kh.numel() * 2, "d2h_bytes_per_step": 2 * out_k.numel() * 2,
-            "path": "pinned host K,V -> H2D -> kvp_*_compress -> D2H K',V'",
+            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 2 * out_k.numel() * 2,
+            "mode": mode,
+            "path": {"serial": "pinned host K,V -> H2D -> kvp_*_compress -> D2H K',V' on one stream",
+                     "staged": "kvpress_b200.host_staging.compress_host: per-kv-head chunks, H2D | kvp_*_compress | D2H "
+                               "on three streams",
+                     "zero_copy": "host_staging.compress_host: K staged per kv-head, kept V rows gathered in place "
+                                  "from pinned host memory by the compaction kernel, D2H overlapped"}[mode],
         }
 
     if rank != 0:

@@ -109,8 +109,16 @@ def _check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what} failed: {msg} (status {rc})")
 
 
-def _require_cuda_kv(keys: torch.Tensor, values: torch.Tensor) -> None:
-    if not (keys.is_cuda and values.is_cuda):
+def _pinned_ok(t: torch.Tensor) -> bool:
+    """A pinned host tensor is addressable from the device (UVA): kernels may gather its rows over PCIe."""
+    return (not t.is_cuda) and t.is_pinned() and torch.cuda.is_available()
+
+
+def _require_cuda_kv(keys: torch.Tensor, values: torch.Tensor, pinned_values: bool = False,
+                     pinned_keys: bool = False) -> None:
+    k_ok = keys.is_cuda or (pinned_keys and _pinned_ok(keys))
+    v_ok = values.is_cuda or (pinned_values and _pinned_ok(values))
+    if not (k_ok and v_ok):
         raise RuntimeError(
             "kvpress_b200 runs on CUDA tensors only (sm_100a kernels); got "
             f"keys on {keys.device}, values on {values.device}. There is no CPU path."
@@ -119,6 +127,10 @@ def _require_cuda_kv(keys: torch.Tensor, values: torch.Tensor) -> None:
         raise RuntimeError(f"kvpress_b200 supports bf16/fp16 caches, got {keys.dtype}/{values.dtype}")
     if keys.dim() != 4 or values.shape != keys.shape:
         raise RuntimeError(f"expected K, V of shape [B, Hkv, S, D], got {tuple(keys.shape)}, {tuple(values.shape)}")
+
+
+def _out_device(keys: torch.Tensor) -> torch.device:
+    return keys.device if keys.is_cuda else torch.device("cuda", torch.cuda.current_device())
 
 
 def _rows_ok(t: torch.Tensor) -> bool:
@@ -132,7 +144,11 @@ def _rows_ok(t: torch.Tensor) -> bool:
 
 def _normalise(t: torch.Tensor) -> torch.Tensor:
     """Strided views are consumed as they are; only layouts the kernels cannot address are copied."""
-    return t if _rows_ok(t) else t.contiguous()
+    if _rows_ok(t):
+        return t
+    if not t.is_cuda:
+        raise RuntimeError("a pinned host K/V view must already have 16-byte aligned, unit-stride rows")
+    return t.contiguous()
 
 
 def _strides(t: torch.Tensor):
@@ -175,10 +191,11 @@ def launches_per_compress(p: KvpProblem, scorer: int) -> int:
 
 def _alloc_out(keys: torch.Tensor, n_kept: int, want_idx: bool, want_scores: bool):
     B, H, S, D = keys.shape
-    k_out = torch.empty((B, H, n_kept, D), dtype=keys.dtype, device=keys.device)
+    dev = _out_device(keys)
+    k_out = torch.empty((B, H, n_kept, D), dtype=keys.dtype, device=dev)
     v_out = torch.empty_like(k_out)
-    idx = torch.empty((B, H, n_kept), dtype=torch.int32, device=keys.device) if want_idx else None
-    scores = torch.empty((B, H, S), dtype=keys.dtype, device=keys.device) if want_scores else None
+    idx = torch.empty((B, H, n_kept), dtype=torch.int32, device=dev) if want_idx else None
+    scores = torch.empty((B, H, S), dtype=keys.dtype, device=dev) if want_scores else None
     return k_out, v_out, idx, scores
 
 
@@ -199,8 +216,9 @@ def knorm_score(keys: torch.Tensor) -> torch.Tensor:
     return scores
 
 
-def knorm_compress(keys, values, n_kept: int, return_indices: bool = False, return_scores: bool = False):
-    _require_cuda_kv(keys, values)
+def knorm_compress(keys, values, n_kept: int, return_indices: bool = False, return_scores: bool = False,
+                   _pinned_values: bool = False):
+    _require_cuda_kv(keys, values, pinned_values=_pinned_values)
     keys, values = _normalise(keys), _normalise(values)
     p = make_problem(keys, values, n_kept)
     k_out, v_out, idx, scores = _alloc_out(keys, n_kept, return_indices, return_scores)
@@ -228,13 +246,14 @@ def streaming_score(keys: torch.Tensor, n_kept: int, n_sink: int) -> torch.Tenso
     return scores
 
 
-def streaming_compress(keys, values, n_kept: int, n_sink: int, return_indices: bool = False):
-    _require_cuda_kv(keys, values)
+def streaming_compress(keys, values, n_kept: int, n_sink: int, return_indices: bool = False,
+                       _pinned_kv: bool = False):
+    _require_cuda_kv(keys, values, pinned_values=_pinned_kv, pinned_keys=_pinned_kv)
     keys, values = _normalise(keys), _normalise(values)
     p = make_problem(keys, values, n_kept)
     k_out, v_out, idx, _ = _alloc_out(keys, n_kept, return_indices, False)
     if n_kept > 0:
-        with torch.cuda.device(keys.device):
+        with torch.cuda.device(k_out.device):
             _check(
                 load().kvp_streaming_compress(
                     ctypes.byref(p), n_sink, _ptr(keys), _ptr(values), _ptr(k_out), _ptr(v_out), _ptr(idx), _stream()),
@@ -273,8 +292,8 @@ def snapkv_score(keys, q_window, window: int, kernel_size: int) -> torch.Tensor:
 
 
 def snapkv_compress(keys, values, q_window, window: int, kernel_size: int, n_kept: int,
-                    return_indices: bool = False, return_scores: bool = False):
-    _require_cuda_kv(keys, values)
+                    return_indices: bool = False, return_scores: bool = False, _pinned_values: bool = False):
+    _require_cuda_kv(keys, values, pinned_values=_pinned_values)
     keys, values = _normalise(keys), _normalise(values)
     q_window = _check_q(q_window, keys, window)
     p = make_problem(keys, values, n_kept, q_window.shape[1])

@@ -531,3 +531,36 @@ def test_key_rerotation_full_size_properties():
     back = torch.cat((lo * c + hi * s, hi * c - lo * s), dim=-1)                          # rotate by -angle
     assert (back - k0.float()).abs().max().item() < 0.08
     assert (back - k0.float()).abs().mean().item() < 0.006
+
+
+@pytest.mark.parametrize("dtype,atol", [(torch.float16, 8e-3), (torch.bfloat16, 6e-2)])
+@pytest.mark.parametrize("variant", ["default", "scaled"])
+def test_key_rerotation_equals_prune_then_rope(dtype, atol, variant):
+    """Semantic check in the spirit of the reference's tests/presses/test_key_rerotation_press_rope.py:20-100:
+    RoPE(all keys) -> prune + re-rotate   must equal   prune(pre-RoPE keys) -> RoPE at positions 0..n_kept-1
+    up to the 16-bit roundings of the two paths ("scaled": a YaRN-like inv_freq and cos/sin scale)."""
+    nat = _native()
+    B, H, S, D = 2, 2, 4096, 64
+    g = torch.Generator().manual_seed(17)
+    pre = (0.5 * torch.randn(B, H, S, D, generator=g)).to(dtype).to(DEV)
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, D, 2).float() / D))
+    scale = 1.0
+    if variant == "scaled":
+        inv_freq = inv_freq / torch.linspace(1.0, 4.0, D // 2)
+        scale = 1.1386
+    inv_freq = inv_freq.to(DEV)
+
+    def rope(x, n):
+        ang = torch.arange(n, device=DEV).float()[:, None] * inv_freq[None, :]
+        emb = torch.cat((ang, ang), dim=-1)
+        cos, sin = (emb.cos() * scale).to(dtype), (emb.sin() * scale).to(dtype)
+        return x * cos + O.rotate_half(x) * sin
+
+    keys = rope(pre, S)
+    values = torch.randn(B, H, S, D, generator=g).to(dtype).to(DEV)
+    scores = torch.rand(B, H, S, generator=g).to(dtype).to(DEV)
+    n_kept = S // 2
+    k2, v2, idx = nat.scores_compress_rerotate(scores, keys, values, n_kept, inv_freq, return_indices=True)
+    expect = rope(_gather_dev(pre, idx.long()), n_kept)
+    assert torch.allclose(k2.float(), expect.float(), atol=atol, rtol=0)
+    assert torch.equal(v2, _gather_dev(values, idx.long()))

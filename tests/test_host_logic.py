@@ -281,3 +281,12 @@ def test_public_surface():
     assert "kv-press-text-generation" in PIPELINE_REGISTRY.get_supported_tasks()
     with pytest.raises(AssertionError):
         ScorerPress(compression_ratio=1.0)
+
+
+def test_host_staging_has_no_cpu_path():
+    """compress_host needs pinned host buffers and a CUDA device; on a CPU-only box it must refuse, not fall back."""
+    from kvpress_b200 import host_staging
+
+    K = torch.randn(1, 2, 64, 64).to(torch.bfloat16)
+    with pytest.raises(RuntimeError, match="pinned"):
+        host_staging.compress_host("knorm", K, K, 32)
