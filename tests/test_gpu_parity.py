@@ -564,3 +564,28 @@ def test_key_rerotation_equals_prune_then_rope(dtype, atol, variant):
     expect = rope(_gather_dev(pre, idx.long()), n_kept)
     assert torch.allclose(k2.float(), expect.float(), atol=atol, rtol=0)
     assert torch.equal(v2, _gather_dev(values, idx.long()))
+
+
+@pytest.mark.parametrize("B,H,G,S", [(1, 8, 4, 40000), (4, 2, 4, 40000), (2, 4, 1, 50000), (3, 2, 2, 60000)])
+def test_expected_attention_compress_matches_its_score_path_large(B, H, G, S):
+    """Multi-batch / multi-head problems well above one wave of tiles: compress with and without scores_out must
+    keep the same rows, the outputs must be exact gathers, and the kept set must be the top-k of the scores."""
+    nat = _native()
+    D, Hq = 128, H * G
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + S)
+    mk = lambda *s: torch.randn(*s, generator=g, device=DEV, dtype=torch.float32)  # noqa: E731
+    K, V = mk(B, H, S, D).to(torch.bfloat16), mk(B, H, S, D).to(torch.bfloat16)
+    mu = (0.5 * mk(B, Hq, D)).to(torch.bfloat16)
+    a = mk(B, Hq, D, D) / D ** 0.5
+    cov = (a @ a.transpose(-1, -2)).to(torch.bfloat16)
+    n_kept = O.kept_count(S, 0.7)
+    k1, v1, i1, _ = nat.expected_attention_compress(K, V, mu, cov, 0.0, 4, True, n_kept, return_indices=True)
+    k2, v2, i2, sc = nat.expected_attention_compress(K, V, mu, cov, 0.0, 4, True, n_kept, return_indices=True,
+                                                     return_scores=True)
+    assert torch.equal(k1, _gather_dev(K, i1)) and torch.equal(v1, _gather_dev(V, i1))
+    assert (i1[..., 1:] > i1[..., :-1]).all()
+    _assert_topk_of_own_scores(sc, i2, n_kept, slice(0, 4))
+    same = torch.zeros(B, H, S, dtype=torch.bool, device=DEV)
+    same.scatter_(2, i1.long(), True)
+    overlap = same.gather(2, i2.long()).float().mean().item()
+    assert overlap > 0.999, overlap
