@@ -4,10 +4,17 @@ CUDA behind the reference's own press API (BasePress / ScorerPress hooks and the
 """
 from kvpress_b200.pipeline import KVPressTextGenerationPipeline
 from kvpress_b200.presses.base_press import SUPPORTED_MODELS, BasePress
+from kvpress_b200.presses.chunk_press import ChunkPress
+from kvpress_b200.presses.composed_press import ComposedPress
+from kvpress_b200.presses.compression_ratio_decoding_press import CompressionRatioDecodingPress
 from kvpress_b200.presses.decoding_press import DecodingPress
 from kvpress_b200.presses.expected_attention_press import ExpectedAttentionPress
 from kvpress_b200.presses.key_rerotation_press import KeyRerotationPress
 from kvpress_b200.presses.knorm_press import KnormPress
+from kvpress_b200.presses.per_layer_compression_press import PerLayerCompressionPress
+from kvpress_b200.presses.prefill_decoding_press import PrefillDecodingPress
+from kvpress_b200.presses.pyramidkv_press import PyramidKVPress
+from kvpress_b200.presses.random_press import RandomPress
 from kvpress_b200.presses.scorer_press import ScorerPress
 from kvpress_b200.presses.snapkv_press import SnapKVPress
 from kvpress_b200.presses.streaming_llm_press import StreamingLLMPress
@@ -21,6 +28,13 @@ __all__ = [
     "StreamingLLMPress",
     "DecodingPress",
     "KeyRerotationPress",
+    "ChunkPress",
+    "ComposedPress",
+    "PerLayerCompressionPress",
+    "PrefillDecodingPress",
+    "CompressionRatioDecodingPress",
+    "PyramidKVPress",
+    "RandomPress",
     "KVPressTextGenerationPipeline",
     "SUPPORTED_MODELS",
 ]

@@ -19,6 +19,7 @@ from transformers.pipelines import PIPELINE_REGISTRY
 
 from kvpress_b200.presses.base_press import BasePress
 from kvpress_b200.presses.decoding_press import DecodingPress
+from kvpress_b200.presses.prefill_decoding_press import PrefillDecodingPress
 
 logger = logging.getLogger(__name__)
 
@@ -82,7 +83,10 @@ class KVPressTextGenerationPipeline(Pipeline):
 
     def _forward(self, input_tensors, max_new_tokens: int = 50, press: Optional[BasePress] = None,
                  cache: Optional[Cache] = None):
-        decoding = isinstance(press, DecodingPress)
+        # pipeline.py:202-230 of the reference: a DecodingPress is live only while generating, a
+        # PrefillDecodingPress in both phases, everything else only during prefill
+        decoding = isinstance(press, (DecodingPress, PrefillDecodingPress))
+        prefilling = press is not None and not isinstance(press, DecodingPress)
         if decoding and len(input_tensors["questions_ids"]) > 1:
             raise ValueError("DecodingPress is not compatible with multiple questions. Please specify a single question.")
 
@@ -91,7 +95,7 @@ class KVPressTextGenerationPipeline(Pipeline):
         if cache is None:
             cache = DynamicCache()
 
-        prefill_ctx = press(self.model) if (press is not None and not decoding) else contextlib.nullcontext()
+        prefill_ctx = press(self.model) if prefilling else contextlib.nullcontext()
         with prefill_ctx:
             self.model.model(input_ids=context_ids, past_key_values=cache)  # no lm_head during prefill
             logger.debug(f"Context Length: {context_length}")

@@ -49,6 +49,17 @@ def layer_is_prefilling(cache, layer_idx: int, q_len: int) -> bool:
     return int(cache.get_seq_length(layer_idx)) == int(q_len)
 
 
+PHASE_KEY = "_kvp_is_prefilling"
+
+
+def hook_is_prefilling(module: nn.Module, kwargs: dict) -> bool:
+    """Phase of this forward call for a hook. A wrapper that chains several presses in one hook (ComposedPress)
+    decides once, before the first press shortens the cache, and pins the answer in kwargs[PHASE_KEY]."""
+    if PHASE_KEY in kwargs:
+        return bool(kwargs[PHASE_KEY])
+    return layer_is_prefilling(kwargs["past_key_values"], module.layer_idx, kwargs["hidden_states"].shape[1])
+
+
 def write_back(cache, layer_idx: int, keys: torch.Tensor, values: torch.Tensor) -> None:
     layer = cache.layers[layer_idx]
     layer.keys = keys
@@ -79,7 +90,7 @@ class BasePress:
         hidden_states = kwargs["hidden_states"]
         cache = kwargs["past_key_values"]
         layer_idx = module.layer_idx
-        if not layer_is_prefilling(cache, layer_idx, hidden_states.shape[1]):
+        if not hook_is_prefilling(module, kwargs):
             return output
         keys, values = extract_keys_and_values(cache, layer_idx)
         keys, values = self.compress(module, hidden_states, keys, values, output[1], kwargs)

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 from transformers import PreTrainedModel
 
-from kvpress_b200.presses.base_press import BasePress, layer_is_prefilling, write_back
+from kvpress_b200.presses.base_press import BasePress, hook_is_prefilling, write_back
 from kvpress_b200.presses.scorer_press import ScorerPress, kept_count
 from kvpress_b200.utils import extract_keys_and_values
 
@@ -101,7 +101,7 @@ class DecodingPress(BasePress):
         cache = kwargs["past_key_values"]
         q_len = hidden_states.shape[1]
         layer_idx = module.layer_idx
-        if layer_is_prefilling(cache, layer_idx, q_len):
+        if hook_is_prefilling(module, kwargs):
             return output  # prefill is some other press's business
 
         buffering = self.hidden_states_buffer_size > 0 and getattr(self.base_press, "needs_hidden_states", True)

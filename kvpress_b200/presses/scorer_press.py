@@ -56,6 +56,10 @@ class ScorerPress(BasePress):
     def _score_is_overridden(self, owner: type) -> bool:
         return type(self).score is not owner.score
 
+    def _n_kept(self, module: nn.Module, k_len: int) -> int:
+        """Positions to keep for this layer (scorer_press.py:93-94); PyramidKV overrides it per layer."""
+        return kept_count(k_len, self.compression_ratio)
+
     def _fused_compress(self, module, hidden_states, keys, values, attentions, kwargs, n_kept):
         """Scorer-specific fused score+select+compact; None means 'use score() + generic select'."""
         return None
@@ -71,7 +75,7 @@ class ScorerPress(BasePress):
     ) -> tuple[torch.Tensor, torch.Tensor]:
         if self.compression_ratio == 0:
             return keys, values
-        n_kept = kept_count(keys.shape[2], self.compression_ratio)
+        n_kept = self._n_kept(module, keys.shape[2])
         fused = self._fused_compress(module, hidden_states, keys, values, attentions, kwargs, n_kept)
         if fused is not None:
             return fused

@@ -176,3 +176,48 @@ def test_key_rerotation_press_through_hook_vs_oracle(model, inner, monkeypatch):
         exact = (ref_k.view(torch.int16) == lc.keys.cpu().view(torch.int16)).float().mean().item()
         assert exact > 0.99, exact
         assert (ref_k.float() - lc.keys.cpu().float()).abs().max().item() <= 2.0 ** -6 * lf.keys.float().abs().max().item()
+
+
+@pytest.mark.parametrize("n_tokens,chunk", [(900, 256), (1024, 256), (700, 1024)])
+def test_chunk_press_on_gpu_matches_per_chunk_oracle(model, n_tokens, chunk):
+    """ChunkPress(KnormPress): all full chunks go through ONE kvp_scores_compress call on the strided
+    [B*H, n_chunks, L, D] view of the cache; the result must be the per-chunk oracle selection, concatenated."""
+    from kvpress_b200 import ChunkPress
+
+    ids = torch.randint(2, 250, (2, n_tokens), device=DEV)
+    full = _full_cache(model, ids)
+    cache = DynamicCache()
+    with ChunkPress(KnormPress(0.5), chunk_length=chunk)(model):
+        model.model(input_ids=ids, past_key_values=cache)
+    for lf, lc in zip(full.layers, cache.layers):
+        K, V = lf.keys.cpu(), lf.values.cpu()
+        ks, vs = [], []
+        for lo in range(0, n_tokens, chunk):
+            kc, vc = K[:, :, lo:lo + chunk], V[:, :, lo:lo + chunk]
+            n_kept = max(1, int(kc.shape[2] * 0.5))
+            idx = O.select_lowest_index_ties(O.knorm_scores(kc), n_kept)
+            ks.append(O.gather_rows(kc, idx))
+            vs.append(O.gather_rows(vc, idx))
+        assert torch.equal(lc.keys.cpu(), torch.cat(ks, dim=2)) and torch.equal(lc.values.cpu(), torch.cat(vs, dim=2))
+
+
+def test_pyramidkv_and_wrappers_on_gpu(model):
+    from kvpress_b200 import ComposedPress, PerLayerCompressionPress, PyramidKVPress, RandomPress
+    from kvpress_b200.presses.pyramidkv_press import pyramid_layer_budget
+
+    ids = torch.randint(2, 250, (2, 800), device=DEV)
+    n_layers = model.config.num_hidden_layers
+    cache = DynamicCache()
+    with PyramidKVPress(0.6, window_size=32, beta=4)(model):
+        model.model(input_ids=ids, past_key_values=cache)
+    assert [la.keys.shape[2] for la in cache.layers] == [pyramid_layer_budget(800, 0.6, 32, 4, n_layers, i)
+                                                         for i in range(n_layers)]
+    cache = DynamicCache()
+    with PerLayerCompressionPress(KnormPress(), [0.25, 0.75][:n_layers] + [0.5] * (n_layers - 2))(model):
+        model.model(input_ids=ids, past_key_values=cache)
+    assert cache.layers[0].keys.shape[2] == 600 and cache.layers[1].keys.shape[2] == 200
+    cache = DynamicCache()
+    press = ComposedPress([RandomPress(0.5, seed=1), KnormPress(0.5)])
+    with press(model):
+        model.model(input_ids=ids, past_key_values=cache)
+    assert cache.get_seq_length() == 200 and press.compression_ratio == pytest.approx(0.75)

@@ -290,3 +290,57 @@ def test_host_staging_has_no_cpu_path():
     K = torch.randn(1, 2, 64, 64).to(torch.bfloat16)
     with pytest.raises(RuntimeError, match="pinned"):
         host_staging.compress_host("knorm", K, K, 32)
+
+
+def test_prefill_decoding_press_runs_both_phases(backend, pipe):
+    """prefill_decoding_press.py:18-103: the prefill press shortens the prompt cache once, the decoding press then
+    keeps the cache inside [target, target + interval) while tokens are generated; decoding state is reset on exit."""
+    from kvpress_b200 import PrefillDecodingPress
+
+    decoding = DecodingPress(base_press=KnormPress(), compression_interval=6, target_size=40)
+    press = PrefillDecodingPress(prefilling_press=KnormPress(0.5), decoding_press=decoding)
+    sizes = []
+    orig = press.forward_hook
+
+    def spy(module, inp, kwargs, output):
+        out = orig(module, inp, kwargs, output)
+        if module.layer_idx == 0:
+            sizes.append(kwargs["past_key_values"].get_seq_length(0))
+        return out
+
+    press.forward_hook = spy
+    context = words(100, seed=20)
+    pipe(context, question=words(3, seed=21), press=press, cache=DynamicCache(), max_new_tokens=24)
+    n_ctx = len(pipe.tokenizer(context)["input_ids"]) if hasattr(pipe.tokenizer(context), "__getitem__") else 100
+    assert sizes[0] == kept_count(n_ctx, 0.5)                  # prefill phase: prefilling_press only
+    assert min(sizes[8:]) >= 40 and max(sizes[8:]) <= 40 + 6 - 1 and 40 in sizes
+    assert decoding.layer_step_counts == {}
+    # either side may be missing
+    only_prefill = PrefillDecodingPress(prefilling_press=KnormPress(0.5))
+    cache = DynamicCache()
+    pipe(context, question=words(3, seed=21), press=only_prefill, cache=cache, max_new_tokens=4)
+    assert cache.get_seq_length() == kept_count(n_ctx, 0.5)
+
+
+def test_compression_ratio_decoding_press_target_follows_tokens_seen(backend, model):
+    """compression_ratio_decoding_press.py:13-50: target = int(tokens_seen * (1 - r)) from position_ids."""
+    from kvpress_b200 import CompressionRatioDecodingPress
+
+    press = CompressionRatioDecodingPress(base_press=KnormPress(), compression_interval=4, target_compression_ratio=0.75)
+    assert press._resolve_target_size({"position_ids": torch.tensor([[198, 199]])}) == 50
+    assert press._resolve_target_size({"position_ids": torch.tensor([[0]])}) == 1
+    with pytest.raises(NotImplementedError):
+        press._resolve_target_size({})
+    with pytest.raises(AssertionError):
+        CompressionRatioDecodingPress(base_press=KnormPress(), target_compression_ratio=1.0)
+    # through the hooks: 60-token prompt, then single-token steps with explicit position_ids
+    ids = torch.randint(2, 250, (1, 60))
+    cache = DynamicCache()
+    with press(model):
+        model.model(input_ids=ids, past_key_values=cache)
+        assert cache.get_seq_length() == 60               # prefill untouched
+        for step in range(8):
+            pos = torch.tensor([[60 + step]])
+            model.model(input_ids=torch.randint(2, 250, (1, 1)), past_key_values=cache, position_ids=pos)
+        # two compactions happened (steps 4 and 8); the last one saw 68 tokens -> int(68 * 0.25) = 17
+        assert cache.get_seq_length() == 17

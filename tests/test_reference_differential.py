@@ -102,3 +102,105 @@ def test_key_rerotation_same_cache_as_reference(monkeypatch, ref, inner, family)
     for lo, lt in zip(ours.layers, theirs.layers):
         assert torch.equal(lo.values, lt.values)
         assert torch.equal(lo.keys, lt.keys)
+
+
+def _prefill_both(ref_press, our_press, model, ids):
+    S = ids.shape[1]
+    theirs, ours = DynamicCache(), DynamicCache()
+    with ref_press(model):
+        model.model(input_ids=ids, past_key_values=theirs, cache_position=torch.arange(S))
+    with our_press(model):
+        model.model(input_ids=ids, past_key_values=ours)
+    return theirs, ours
+
+
+def _distinct_ids(seed, n=160, batch=2):
+    g = torch.Generator().manual_seed(seed)
+    return torch.stack([torch.randperm(250, generator=g)[:n] + 2 for _ in range(batch)])
+
+
+def _assert_same_rows(ours, theirs):
+    for lo, lt in zip(ours.layers, theirs.layers):
+        assert lo.keys.shape == lt.keys.shape
+        assert torch.allclose(_rows_signature(lo.keys, lo.values), _rows_signature(lt.keys, lt.values), atol=1e-9)
+
+
+@pytest.mark.parametrize("ratio,beta", [(0.3, 20), (0.6, 4), (0.5, 1), (0.9, 20)])
+def test_pyramidkv_same_rows_and_budgets_as_reference(monkeypatch, ref, ratio, beta):
+    """pyramidkv_press.py:47-112: per-layer budgets (incl. the fallback branch) and the kept rows."""
+    from kvpress_b200 import PyramidKVPress
+    from kvpress_b200.presses.pyramidkv_press import pyramid_layer_budget
+
+    cpu_backend.install(monkeypatch)
+    model = tiny_llama(layers=4)
+    ids = _distinct_ids(11)
+    kw = dict(compression_ratio=ratio, window_size=16, kernel_size=5, beta=beta)
+    theirs, ours = _prefill_both(ref.PyramidKVPress(**kw), PyramidKVPress(**kw), model, ids)
+    lens = [layer.keys.shape[2] for layer in ours.layers]
+    assert lens == [layer.keys.shape[2] for layer in theirs.layers]
+    n_layers = model.config.num_hidden_layers
+    assert lens == [pyramid_layer_budget(160, ratio, 16, beta, n_layers, i) for i in range(n_layers)]
+    _assert_same_rows(ours, theirs)
+    # the budget formula alone, over a grid, against the reference method
+    from types import SimpleNamespace
+    for q_len in (100, 777, 4096, 131072):
+        for r in (0.1, 0.5, 0.75, 0.95):
+            for b in (1, 5, 20):
+                for layer in (0, 7, 31):
+                    mod = SimpleNamespace(config=SimpleNamespace(num_hidden_layers=32), layer_idx=layer)
+                    want = ref.PyramidKVPress(compression_ratio=r, window_size=64, beta=b).get_layer_budget(mod, q_len)
+                    assert pyramid_layer_budget(q_len, r, 64, b, 32, layer) == want
+
+
+@pytest.mark.parametrize("inner", ["knorm", "snapkv"])
+@pytest.mark.parametrize("n_tokens,chunk", [(160, 40), (150, 64), (100, 256)])
+def test_chunk_press_same_rows_as_reference(monkeypatch, ref, inner, n_tokens, chunk):
+    from kvpress_b200 import ChunkPress
+
+    cpu_backend.install(monkeypatch)
+    model = tiny_llama()
+    ids = _distinct_ids(12, n=n_tokens)
+    _, ref_cls, our_cls, kw = next(c for c in CASES if c[0] == inner)
+    if inner == "snapkv":
+        kw = {"window_size": 8, "kernel_size": 3}
+    theirs, ours = _prefill_both(ref.ChunkPress(ref_cls(ref)(compression_ratio=0.5, **kw), chunk_length=chunk),
+                                 ChunkPress(our_cls(compression_ratio=0.5, **kw), chunk_length=chunk), model, ids)
+    assert ours.get_seq_length() == theirs.get_seq_length()
+    _assert_same_rows(ours, theirs)
+
+
+def test_composed_and_per_layer_wrappers_same_rows_as_reference(monkeypatch, ref):
+    from kvpress_b200 import ComposedPress, PerLayerCompressionPress
+
+    cpu_backend.install(monkeypatch)
+    model = tiny_llama()
+    ids = _distinct_ids(13)
+    # second press = Knorm: its scores do not depend on the ROW ORDER the first press leaves behind (the reference
+    # emits top-k order, this package ascending positions; index-based scorers such as SnapKV's window or
+    # StreamingLLM's sinks would read a different "last w rows" from the reference's permuted cache)
+    rp = ref.ComposedPress([ref.SnapKVPress(0.25, window_size=16), ref.KnormPress(0.4)])
+    op = ComposedPress([SnapKVPress(0.25, window_size=16), KnormPress(0.4)])
+    theirs, ours = _prefill_both(rp, op, model, ids)
+    assert ours.get_seq_length() == theirs.get_seq_length()
+    assert op.compression_ratio == pytest.approx(rp.compression_ratio)
+    _assert_same_rows(ours, theirs)
+
+    ratios = [0.2, 0.6][: model.config.num_hidden_layers] + [0.5] * max(0, model.config.num_hidden_layers - 2)
+    rp = ref.PerLayerCompressionPress(ref.SnapKVPress(window_size=16), ratios)
+    op = PerLayerCompressionPress(SnapKVPress(window_size=16), ratios)
+    theirs, ours = _prefill_both(rp, op, model, ids)
+    assert [la.keys.shape[2] for la in ours.layers] == [la.keys.shape[2] for la in theirs.layers]
+    assert op.compression_ratio == pytest.approx(rp.compression_ratio)
+    with pytest.raises(AttributeError):
+        op.compression_ratio = 0.1
+    _assert_same_rows(ours, theirs)
+
+
+def test_random_press_same_rows_as_reference_on_cpu(monkeypatch, ref):
+    from kvpress_b200 import RandomPress
+
+    cpu_backend.install(monkeypatch)
+    model = tiny_llama()
+    ids = _distinct_ids(14)
+    theirs, ours = _prefill_both(ref.RandomPress(0.5, seed=3), RandomPress(0.5, seed=3), model, ids)
+    _assert_same_rows(ours, theirs)
