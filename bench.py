@@ -46,6 +46,9 @@ WORKLOADS = {
     # KeyRerotationPress(KnormPress): score + select + compaction with re-rotated keys
     "rerotate_knorm_128k": dict(scorer="knorm_rerotate", B=1, Hkv=8, Hq=8, S=131072, D=128, ratio=0.5,
                                 config_index=None, label="KeyRerotationPress(KnormPress) r=0.5, 128k ctx"),
+    # AdaKVPress(ExpectedAttentionPress): EA scores, then the two head-wise selections (no compaction)
+    "adakv_ea_128k": dict(scorer="adakv_ea", B=1, Hkv=8, Hq=32, S=131072, D=128, ratio=0.7, config_index=None,
+                          label="AdaKVPress(ExpectedAttentionPress) r=0.7 head-wise selection, 128k ctx"),
     "streaming_128k": dict(scorer="streaming", B=1, Hkv=8, Hq=8, S=131072, D=128, ratio=0.5, config_index=None,
                            label="StreamingLLMPress r=0.5, 128k ctx"),
     # steady state of configs[3]: DecodingPress(Knorm, 512, 2048) compaction 2560 -> 2048
@@ -66,6 +69,7 @@ def algorithmic_bytes(w: dict, n_kept: int) -> int:
     per_head = {
         "knorm": row * (S + 3 * n_kept),
         "knorm_rerotate": row * (S + 3 * n_kept),
+        "adakv_ea": row * 2 * S,  # read all K and all V once; the output is index triples only
         "snapkv": row * (S + 3 * n_kept),
         "expected_attention": row * (2 * S + 2 * n_kept),
         "streaming": row * 4 * n_kept,
@@ -122,7 +126,7 @@ def make_inputs(w: dict, device, seed: int, pinned_host: bool = False):
         extra["inv_freq"] = 1.0 / (500000.0 ** (torch.arange(0, D, 2).float() / D))  # Llama-3 rope_theta
     if w["scorer"] == "snapkv":
         extra["q_window"] = torch.randn((B, Hq, 64, D), generator=g, dtype=torch.float32).to(torch.bfloat16)
-    if w["scorer"] == "expected_attention":
+    if w["scorer"] in ("expected_attention", "adakv_ea"):
         extra["mu"] = (0.5 * torch.randn((B, Hq, D), generator=g)).to(torch.bfloat16)
         a = torch.randn((B, Hq, D, D), generator=g) / D ** 0.5
         extra["cov"] = (a @ a.transpose(-1, -2)).to(torch.bfloat16)  # PSD like a real covariance
@@ -139,6 +143,12 @@ def run_native(w: dict, K, V, extra, n_kept: int):
         return native.knorm_compress(K, V, n_kept)[:2]
     if s == "knorm_rerotate":
         return native.scores_compress_rerotate(native.knorm_score(K), K, V, n_kept, extra["inv_freq"])[:2]
+    if s == "adakv_ea":
+        sc = native.expected_attention_score(K, V, extra["mu"], extra["cov"], 1e-2, 4, True)
+        n_safe = int(n_kept * 0.2)
+        sc = sc.scatter(-1, native.scores_select(sc, n_safe).long(), torch.finfo(sc.dtype).max)
+        H, S = sc.shape[1], sc.shape[2]
+        return native.scores_select((-sc).reshape(sc.shape[0], 1, H * S), H * (S - n_kept)), None
     if s == "streaming":
         return native.streaming_compress(K, V, n_kept, 4)[:2]
     if s == "snapkv":
@@ -157,6 +167,12 @@ def run_oracle(w: dict, K, V, extra, ratio: float):
     if s == "knorm_rerotate":
         n_kept = O.kept_count(K.shape[2], ratio)
         return O.key_rerotation_compress(O.knorm_scores(K), K, V, n_kept, extra["inv_freq"])[:2]
+    if s == "adakv_ea":
+        sc = O.expected_attention_scores(K, V, extra["mu"], extra["cov"], 1e-2, 4, True)
+        n_kept = O.kept_count(K.shape[2], ratio)
+        sc = sc.scatter(-1, sc.topk(int(n_kept * 0.2), dim=-1).indices, torch.finfo(sc.dtype).max)
+        H, S = sc.shape[1], sc.shape[2]
+        return torch.topk(-sc.reshape(sc.shape[0], -1), H * (S - n_kept), dim=1).indices, None
     if s == "streaming":
         return O.streaming_compress(K, V, ratio, 4)
     if s == "snapkv":
@@ -236,7 +252,7 @@ def cpu_leg(w: dict, budget_s: float, max_reps: int = 3):
     torch.set_num_threads(os.cpu_count() or 1)
     ratio = effective_ratio(w)
     # rough cost model (ms per 1k tokens on ~8 cores) to size the sample without trial runs
-    per_k = {"knorm": 3.5, "knorm_rerotate": 6.0, "streaming": 3.0, "snapkv": 16.0, "expected_attention": 50.0}[w["scorer"]]
+    per_k = {"knorm": 3.5, "knorm_rerotate": 6.0, "adakv_ea": 50.0, "streaming": 3.0, "snapkv": 16.0, "expected_attention": 50.0}[w["scorer"]]
     S = w["S"]
     while S > 4096 and per_k * S / 1000 / 1000 * max_reps > budget_s:
         S //= 2
@@ -376,6 +392,8 @@ def main():
     p = native.make_problem(sets[0][0], sets[0][1], n_kept, w["Hq"])
     if w["scorer"] == "knorm_rerotate":  # kvp_knorm_score (1) + kvp_scores_compress_rerotate (generic: 3)
         launches = 1 + native.launches_per_compress(p, 0)
+    elif w["scorer"] == "adakv_ea":  # EA score (memset, logits, vnorm, finalize, sentinel) + 2 x kvp_scores_select (3 each)
+        launches = 5 + 2 * native.launches_per_compress(p, 0)
     else:
         scorer_id = {"knorm": 1, "streaming": 2, "snapkv": 3, "expected_attention": 4}[w["scorer"]]
         launches = native.launches_per_compress(p, scorer_id)
@@ -401,6 +419,7 @@ def main():
         Kh, Vh, extra_h = make_inputs(w, device, 99 + rank, pinned_host=True)
         out_k = torch.empty((w["B"], w["Hkv"], n_kept, w["D"]), dtype=torch.bfloat16).pin_memory()
         out_v = torch.empty_like(out_k).pin_memory()
+        out_idx = torch.empty(w["B"] * w["Hkv"] * (w["S"] - n_kept), dtype=torch.int32).pin_memory()
         e2e_steps = max(2, min(args.steps, 8))
 
         from kvpress_b200 import host_staging
@@ -408,8 +427,10 @@ def main():
         mode = args.e2e_mode
         if mode == "auto":
             # measured (profiles/r01_e2e_modes.txt): zero_copy > staged > serial wherever V is not read to score
-            mode = {"knorm_rerotate": "serial", "expected_attention": "staged"}.get(w["scorer"], "zero_copy")
-        if mode == "zero_copy" and w["scorer"] in ("expected_attention", "knorm_rerotate"):
+            mode = {"knorm_rerotate": "serial", "adakv_ea": "serial", "expected_attention": "staged"}.get(w["scorer"], "zero_copy")
+        if mode != "serial" and w["scorer"] in ("knorm_rerotate", "adakv_ea"):
+            raise SystemExit("this workload only has the serial host path")
+        if mode == "zero_copy" and w["scorer"] == "expected_attention":
             raise SystemExit("zero_copy needs a scorer that does not read V to score")
 
         extra_pinned = {k: v.cpu().pin_memory() for k, v in extra_h.items()}  # small operands travel every step too
@@ -420,6 +441,9 @@ def main():
                 Kd = Kh.to(device, non_blocking=True)
                 Vd = Vh.to(device, non_blocking=True)
                 k2, v2 = run_native(w, Kd, Vd, extra_d, n_kept)
+                if v2 is None:  # head-wise selection: the result is the pruned index list
+                    out_idx.copy_(k2.reshape(-1), non_blocking=True)
+                    return
                 out_k.copy_(k2, non_blocking=True)
                 out_v.copy_(v2, non_blocking=True)
                 return
@@ -447,7 +471,7 @@ def main():
                                            else Kh.numel() * 2 + out_v.numel() * 2)}[mode]
         e2e = {
             "value": tokens_per_step / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
-            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 2 * out_k.numel() * 2,
+            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": (out_idx.numel() * 4 if w["scorer"] == "adakv_ea" else 2 * out_k.numel() * 2),
             "mode": mode,
             "path": {"serial": "pinned host K,V -> H2D -> kvp_*_compress -> D2H K',V' on one stream",
                      "staged": "kvpress_b200.host_staging.compress_host: per-kv-head chunks, H2D | kvp_*_compress | D2H "

@@ -144,6 +144,13 @@ int kvp_scores_compress(const kvp_problem* p, const void* scores, const int64_t*
                         int32_t* idx_out, void* workspace, size_t workspace_bytes,
                         kvp_stream_t stream);
 
+/* ---- selection only: the n_kept best positions of every [S] score row, ascending, into idx_out
+ * [B, Hkv, n_kept]; no K/V are touched (p->D and the K/V strides are ignored). What head-wise presses need:
+ * AdaKVPress (kvpress/presses/adakv_press.py:53-78) = this call on the [B, Hkv, S] scores with n_safe, then
+ * on the negated, head-flattened [B, 1, Hkv*S] scores with the number of positions to prune. */
+int kvp_scores_select(const kvp_problem* p, const void* scores, const int64_t* score_stride,
+                      int32_t* idx_out, void* workspace, size_t workspace_bytes, kvp_stream_t stream);
+
 /* ---- KeyRerotationPress (first "next" row): same selection as kvp_scores_compress, but each
  * kept key is re-rotated from its original position s to its new position j (kvpress/presses/
  * key_rerotation_press.py:50-152): k * cos((j-s) inv_freq) + rotate_half(k) * sin((j-s) inv_freq).

@@ -3,6 +3,7 @@ CUDA behind the reference's own press API (BasePress / ScorerPress hooks and the
 "kv-press-text-generation" pipeline). See DESIGN.md for scope and INTEGRATION.md for the C ABI.
 """
 from kvpress_b200.pipeline import KVPressTextGenerationPipeline
+from kvpress_b200.presses.adakv_press import AdaKVPress
 from kvpress_b200.presses.base_press import SUPPORTED_MODELS, BasePress
 from kvpress_b200.presses.chunk_press import ChunkPress
 from kvpress_b200.presses.composed_press import ComposedPress
@@ -28,6 +29,7 @@ __all__ = [
     "StreamingLLMPress",
     "DecodingPress",
     "KeyRerotationPress",
+    "AdaKVPress",
     "ChunkPress",
     "ComposedPress",
     "PerLayerCompressionPress",

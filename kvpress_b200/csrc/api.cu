@@ -352,6 +352,25 @@ int kvp_scores_compress(const kvp_problem* p, const void* scores, const int64_t*
     return select_and_compact(d, K, V, K_out, V_out, idx_out, ws, st);
 }
 
+int kvp_scores_select(const kvp_problem* p, const void* scores, const int64_t* score_stride,
+                      int32_t* idx_out, void* workspace, size_t workspace_bytes, kvp_stream_t stream) {
+    Dims d;
+    int rc = validate(p, &d, false);
+    if (rc) return rc;
+    if (d.n_kept == 0) return KVP_OK;
+    if (!scores || !score_stride || !idx_out) return KVP_ERR_NULL_POINTER;
+    Workspace ws;
+    WsLayout L;
+    if ((rc = carve(d, KVP_SCORER_GENERIC, 0, workspace, workspace_bytes, &ws, &L))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(ws.hist_hi, 0, L.hist_bytes, st);
+    if (e != cudaSuccess) return fail_cuda(e);
+    e = launch_keys_from_scores(d, p->dtype, scores, score_stride[0], score_stride[1], ws, st);
+    if (e != cudaSuccess) return fail_cuda(e);
+    d.ks = d.vs = {0, 0, 0};
+    return select_and_compact(d, nullptr, nullptr, nullptr, nullptr, idx_out, ws, st);
+}
+
 int kvp_scores_compress_rerotate(const kvp_problem* p, const void* scores, const int64_t* score_stride,
                                  const void* K, const void* V, const float* inv_freq, void* K_out,
                                  void* V_out, int32_t* idx_out, void* workspace,

@@ -420,7 +420,9 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
         const int64_t row_bytes = (int64_t)D * 2;
         const char* k_src = K + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2;
         const char* v_src = V + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2;
-        if constexpr (std::is_void<TR>::value) {
+        if (K_out == nullptr) {
+            // selection only (kvp_scores_select): the kept positions in idx_out are the whole result
+        } else if constexpr (std::is_void<TR>::value) {
             copy_rows_kv<KVP_SEL_U, KVP_SEL_TWO>(k_src, ks.s * 2, v_src, vs.s * 2, K_out + out_row0 * row_bytes,
                                                  V_out + out_row0 * row_bytes, row_bytes, sm.list, count, D >> 3);
         } else {

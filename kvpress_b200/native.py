@@ -65,6 +65,7 @@ SIGNATURES = {
         ctypes.c_int, [_PP, _P, _P, _P, _P, ctypes.c_float, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "kvp_scores_compress": (
         ctypes.c_int, [_PP, _P, ctypes.POINTER(ctypes.c_int64), _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "kvp_scores_select": (ctypes.c_int, [_PP, _P, ctypes.POINTER(ctypes.c_int64), _P, _P, _SZ, _P]),
     "kvp_scores_compress_rerotate": (
         ctypes.c_int, [_PP, _P, ctypes.POINTER(ctypes.c_int64), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "kvp_host_workspace_bytes": (ctypes.c_int, [_PP, ctypes.c_int, ctypes.POINTER(_SZ)]),
@@ -387,6 +388,26 @@ def scores_compress(scores: torch.Tensor, keys, values, n_kept: int, return_indi
                 "kvp_scores_compress",
             )
     return k_out, v_out, idx
+
+
+def scores_select(scores: torch.Tensor, n_kept: int) -> torch.Tensor:
+    """Positions of the n_kept largest scores of every row of a [B, H, S] bf16/fp16 CUDA tensor, ascending
+    (ties to the lowest positions), int32 [B, H, n_kept]. No K/V involved."""
+    if not scores.is_cuda or scores.dtype not in _DTYPES or scores.dim() != 3:
+        raise RuntimeError(f"scores must be a CUDA bf16/fp16 [B, H, S] tensor, got {scores.dtype} on {scores.device}")
+    if scores.stride(2) != 1:
+        scores = scores.contiguous()
+    B, H, S = scores.shape
+    p = KvpProblem()
+    p.B, p.Hkv, p.Hq, p.S, p.D, p.n_kept, p.dtype = B, H, H, S, 8, int(n_kept), _DTYPES[scores.dtype]
+    idx = torch.empty((B, H, n_kept), dtype=torch.int32, device=scores.device)
+    if n_kept > 0:
+        sstride = (ctypes.c_int64 * 2)(scores.stride(0) if B > 1 else 0, scores.stride(1) if H > 1 else 0)
+        with torch.cuda.device(scores.device):
+            ws = _workspace(p, SCORER_GENERIC, scores.device)
+            _check(load().kvp_scores_select(ctypes.byref(p), _ptr(scores), sstride, _ptr(idx), _ptr(ws), ws.numel(),
+                                            _stream()), "kvp_scores_select")
+    return idx
 
 
 def scores_compress_rerotate(scores: torch.Tensor, keys, values, n_kept: int, inv_freq: torch.Tensor,

@@ -589,3 +589,60 @@ def test_expected_attention_compress_matches_its_score_path_large(B, H, G, S):
     same.scatter_(2, i1.long(), True)
     overlap = same.gather(2, i2.long()).float().mean().item()
     assert overlap > 0.999, overlap
+
+
+# ---------------------------------------------------------------------------------------------------
+# selection only (kvp_scores_select) and AdaKV's two-stage head-wise selection
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,n_kept", [((2, 4, 3000), 700), ((1, 1, 8 * 40000), 123457), ((3, 2, 257), 257),
+                                          ((1, 8, 131072), 1), ((2, 1, 1000), 0)])
+@pytest.mark.parametrize("kind", ["random", "ties"])
+def test_scores_select_vs_oracle(shape, n_kept, kind):
+    nat = _native()
+    g = torch.Generator().manual_seed(shape[2] + n_kept)
+    scores = torch.randn(shape, generator=g)
+    if kind == "ties":
+        scores = (scores * 2).round() / 2
+    scores = scores.to(torch.bfloat16)
+    idx = nat.scores_select(scores.to(DEV), n_kept)
+    assert idx.dtype == torch.int32 and tuple(idx.shape) == (*shape[:2], n_kept)
+    assert torch.equal(idx.long().cpu(), O.select_lowest_index_ties(scores, n_kept))
+
+
+def test_adakv_selection_at_128k():
+    """AdaKVPress.compress on a [1, 8, 131072] score tensor: budgets, safeguard, and every pruned score is <= every
+    unprotected kept score (tie-aware), checked against a straightforward torch evaluation on the device."""
+    from types import SimpleNamespace
+
+    from kvpress_b200 import AdaKVPress, ScorerPress
+
+    B, H, S, ratio, alpha = 1, 8, 131072, 0.7, 0.2
+    g = torch.Generator(device=DEV).manual_seed(5)
+    # heads with very different score scales so that the cross-head selection is far from uniform
+    scores = (torch.randn(B, H, S, generator=g, device=DEV) * torch.logspace(-1, 1, H, device=DEV)[None, :, None])
+    scores = scores.to(torch.bfloat16)
+
+    class Fixed(ScorerPress):
+        def score(self, *a):
+            return scores.clone()
+
+    module = SimpleNamespace(config=SimpleNamespace(_attn_implementation="sdpa"))
+    K = torch.empty(B, H, S, 8, device=DEV, dtype=torch.bfloat16)
+    press = AdaKVPress(Fixed(compression_ratio=ratio), alpha_safeguard=alpha)
+    k2, v2 = press.compress(module, None, K, K, None, {})
+    assert k2 is K and v2 is K
+    b, h, s = module.masked_key_indices
+    n_kept = O.kept_count(S, ratio)
+    n_safe = int(n_kept * alpha)
+    assert b.numel() == H * (S - n_kept)
+    pruned = torch.zeros(B, H, S, dtype=torch.bool, device=DEV)
+    pruned[b, h, s] = True
+    assert pruned.sum().item() == H * (S - n_kept)                       # triples are distinct
+    kept_per_head = (~pruned).sum(-1)
+    assert (kept_per_head >= n_safe).all() and kept_per_head.float().std().item() > 100
+    # safeguard: the n_safe best positions of every head (canonical tie rule) survive
+    safe = O.select_lowest_index_ties(scores.cpu(), n_safe).to(DEV)
+    assert not pruned.gather(-1, safe).any()
+    # every pruned score <= every kept, unprotected score
+    boosted = scores.float().scatter(-1, safe, float("inf"))
+    assert boosted[pruned].max().item() <= boosted[~pruned].min().item()

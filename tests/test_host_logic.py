@@ -344,3 +344,52 @@ def test_compression_ratio_decoding_press_target_follows_tokens_seen(backend, mo
             model.model(input_ids=torch.randint(2, 250, (1, 1)), past_key_values=cache, position_ids=pos)
         # two compactions happened (steps 4 and 8); the last one saw 68 tokens -> int(68 * 0.25) = 17
         assert cache.get_seq_length() == 17
+
+
+@torch.no_grad()
+def test_adakv_fake_keys_equal_an_explicit_per_head_mask(backend, model):
+    """attention_patch.py: overwriting the pruned keys of a head with the hyperplane fake key must give the same
+    decoding step as masking those (head, position) pairs with -inf. Also checks the AdaKV budget arithmetic."""
+    import copy
+
+    from kvpress_b200 import AdaKVPress
+
+    ids = torch.randint(2, 250, (2, 90))
+    S, H, G = 90, model.config.num_key_value_heads, model.config.num_attention_heads // model.config.num_key_value_heads
+    press = AdaKVPress(KnormPress(0.6), alpha_safeguard=0.25)
+    cache = DynamicCache()
+    attns = [layer.self_attn for layer in model.model.layers]
+    with press(model):
+        model.model(input_ids=ids, past_key_values=cache)
+        masks = [a.masked_key_indices for a in attns]
+        n_kept = kept_count(S, 0.6)
+        for b, h, s in masks:
+            assert b.numel() == 2 * H * (S - n_kept)
+            pruned_per_head = torch.zeros(2, H, dtype=torch.long).index_put_((b, h), torch.ones_like(b), accumulate=True)
+            assert (S - pruned_per_head >= int(n_kept * 0.25)).all()        # safeguard: every head keeps n_safe
+            assert pruned_per_head.sum(1).eq(H * (S - n_kept)).all()         # same total budget per batch element
+        patched_cache = copy.deepcopy(cache)
+        y_patch = model.model(input_ids=ids[:, :1], past_key_values=patched_cache).last_hidden_state
+    for a in attns:
+        a.masked_key_indices = None
+
+    # the same step with an explicit additive mask per layer (q-heads of a kv-head share its mask)
+    layer_masks = []
+    for b, h, s in masks:
+        m = torch.zeros(2, H, 1, S + 1)
+        m[b, h, 0, s] = float("-inf")
+        layer_masks.append(m.repeat_interleave(G, dim=1))
+    handles = []
+    for a, m in zip(attns, layer_masks):
+        def pre(module, args, kwargs, m=m):
+            kwargs["attention_mask"] = m
+            return args, kwargs
+        handles.append(a.register_forward_pre_hook(pre, with_kwargs=True))
+    try:
+        y_mask = model.model(input_ids=ids[:, :1], past_key_values=copy.deepcopy(cache)).last_hidden_state
+    finally:
+        for hd in handles:
+            hd.remove()
+    y_plain = model.model(input_ids=ids[:, :1], past_key_values=copy.deepcopy(cache)).last_hidden_state
+    assert torch.allclose(y_patch, y_mask, atol=1e-5)
+    assert not torch.allclose(y_patch, y_plain, atol=1e-4)

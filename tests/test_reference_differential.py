@@ -204,3 +204,46 @@ def test_random_press_same_rows_as_reference_on_cpu(monkeypatch, ref):
     ids = _distinct_ids(14)
     theirs, ours = _prefill_both(ref.RandomPress(0.5, seed=3), RandomPress(0.5, seed=3), model, ids)
     _assert_same_rows(ours, theirs)
+
+
+@pytest.mark.parametrize("inner", ["expected_attention", "snapkv"])
+@pytest.mark.parametrize("alpha", [0.2, 0.0, 1.0])
+def test_adakv_masks_the_same_keys_as_reference(monkeypatch, ref, inner, alpha):
+    """adakv_press.py:53-78: per-head safeguard + bottom-k across heads; the pruned (batch, head, position)
+    triples must be the reference's, and one decoding step through attention_patch must give the same output."""
+    from kvpress_b200 import AdaKVPress
+
+    cpu_backend.install(monkeypatch)
+    model = tiny_llama()
+    ids = _distinct_ids(21)
+    S = ids.shape[1]
+    _, ref_cls, our_cls, kw = next(c for c in CASES if c[0] == inner)
+    attns = [layer.self_attn for layer in model.model.layers]
+
+    def masks():
+        out = []
+        for a in attns:
+            b, h, s = a.masked_key_indices
+            out.append(set(zip(b.tolist(), h.tolist(), s.tolist())))
+        return out
+
+    def run(press, with_cache_position):
+        cache = DynamicCache()
+        with press(model):
+            extra = {"cache_position": torch.arange(S)} if with_cache_position else {}
+            model.model(input_ids=ids, past_key_values=cache, **extra)
+            m = masks()
+            extra = {"cache_position": torch.tensor([S])} if with_cache_position else {}
+            step = model.model(input_ids=ids[:, :1], past_key_values=cache, **extra).last_hidden_state
+        for a in attns:
+            a.masked_key_indices = None
+        return cache, m, step
+
+    c_ref, m_ref, y_ref = run(ref.AdaKVPress(ref_cls(ref)(compression_ratio=0.5, **kw), alpha_safeguard=alpha), True)
+    c_our, m_our, y_our = run(AdaKVPress(our_cls(compression_ratio=0.5, **kw), alpha_safeguard=alpha), False)
+    H = model.config.num_key_value_heads
+    for a, b in zip(m_our, m_ref):
+        assert len(a) == len(b) == ids.shape[0] * H * (S - int(S * 0.5))
+        assert a == b
+    assert c_our.get_seq_length() == c_ref.get_seq_length() == S + 1      # AdaKV never shrinks the cache
+    assert torch.allclose(y_our, y_ref, atol=1e-5)
