@@ -440,8 +440,11 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
 // flag), items [nA, nA + nB) the compact items (last rows / last tiles first, so K rows the score
 // stage touched last are re-read while still in L2). A compact item only waits for refine items,
 // which precede it in the queue and never wait themselves => no deadlock for any grid size.
+#ifndef KVP_REROT_CTAS
+#define KVP_REROT_CTAS 4  // re-rotating variant: 64 regs, 4 CTAs/SM (issue-bound on sincosf; A/B 220 -> 207 us, profiles/r01_ab_rerot.txt)
+#endif
 template <typename TR>
-__global__ void __launch_bounds__(kTileThreads, KVP_SEL_CTAS)
+__global__ void __launch_bounds__(kTileThreads, std::is_void<TR>::value ? KVP_SEL_CTAS : KVP_REROT_CTAS)
 select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, Strides3 ks,
                       Strides3 vs, char* __restrict__ K_out, char* __restrict__ V_out,
                       int32_t* __restrict__ idx_out, int H, int S, int D, int n_kept,

@@ -9,7 +9,7 @@ from kvpress_b200 import native
 import bench
 native.load()
 out = []
-for wl in ("ea_128k", "knorm_128k"):
+for wl in os.environ.get("AB_WORKLOADS", "ea_128k,knorm_128k").split(","):
     w = bench.WORKLOADS[wl]
     K, V, extra = bench.make_inputs(w, "cuda:0", 1)
     n_kept = bench.kept_count(w["S"], w["ratio"])
