@@ -68,7 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(f"nvcc failed on {src}\n")
     if failed:
         raise RuntimeError("kvpress_b200: CUDA build failed")
-    link = [nvcc, "-shared", "-cudart", "static", "-o", str(LIB_PATH), *objs]
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", str(LIB_PATH), *objs]
     subprocess.run(link, check=True)
     STAMP.write_text(fp)
     return LIB_PATH
