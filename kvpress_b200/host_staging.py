@@ -87,8 +87,8 @@ def compress_host(scorer: str, keys_host: torch.Tensor, values_host: torch.Tenso
         return out_keys, out_values
     if values_zero_copy is None:
         values_zero_copy = False
-    if values_zero_copy and scorer == "expected_attention" and params.get("use_vnorm", True):
-        raise RuntimeError("values_zero_copy needs a scorer that does not read V to score")
+    if values_zero_copy and scorer == "expected_attention":
+        raise RuntimeError("values_zero_copy needs a scorer that does not read V to score (Knorm, SnapKV, StreamingLLM)")
     Hq = num_q_heads or {"snapkv": lambda: params["q_window"].shape[1],
                          "expected_attention": lambda: params["mu"].shape[1]}.get(scorer, lambda: H)()
     G = Hq // H
