@@ -49,6 +49,9 @@ WORKLOADS = {
     # AdaKVPress(ExpectedAttentionPress): EA scores, then the two head-wise selections (no compaction)
     "adakv_ea_128k": dict(scorer="adakv_ea", B=1, Hkv=8, Hq=32, S=131072, D=128, ratio=0.7, config_index=None,
                           label="AdaKVPress(ExpectedAttentionPress) r=0.7 head-wise selection, 128k ctx"),
+    # KeyDiffPress (two streaming passes over K, then select + compact)
+    "keydiff_128k": dict(scorer="keydiff", B=1, Hkv=8, Hq=8, S=131072, D=128, ratio=0.5, config_index=None,
+                         label="KeyDiffPress r=0.5, Llama-3.1-8B layer shape, 128k ctx"),
     "streaming_128k": dict(scorer="streaming", B=1, Hkv=8, Hq=8, S=131072, D=128, ratio=0.5, config_index=None,
                            label="StreamingLLMPress r=0.5, 128k ctx"),
     # steady state of configs[3]: DecodingPress(Knorm, 512, 2048) compaction 2560 -> 2048
@@ -69,6 +72,7 @@ def algorithmic_bytes(w: dict, n_kept: int) -> int:
     per_head = {
         "knorm": row * (S + 3 * n_kept),
         "knorm_rerotate": row * (S + 3 * n_kept),
+        "keydiff": row * (2 * S + 3 * n_kept),  # the anchor needs all of K before any score: K is read twice
         "adakv_ea": row * 2 * S,  # read all K and all V once; the output is index triples only
         "snapkv": row * (S + 3 * n_kept),
         "expected_attention": row * (2 * S + 2 * n_kept),
@@ -141,6 +145,8 @@ def run_native(w: dict, K, V, extra, n_kept: int):
     s = w["scorer"]
     if s == "knorm":
         return native.knorm_compress(K, V, n_kept)[:2]
+    if s == "keydiff":
+        return native.keydiff_compress(K, V, n_kept)[:2]
     if s == "knorm_rerotate":
         return native.scores_compress_rerotate(native.knorm_score(K), K, V, n_kept, extra["inv_freq"])[:2]
     if s == "adakv_ea":
@@ -164,6 +170,10 @@ def run_oracle(w: dict, K, V, extra, ratio: float):
     s = w["scorer"]
     if s == "knorm":
         return O.knorm_compress(K, V, ratio)
+    if s == "keydiff":
+        n_kept = O.kept_count(K.shape[2], ratio)
+        idx = O.topk_indices(O.keydiff_scores(K), n_kept)
+        return O.gather_rows(K, idx), O.gather_rows(V, idx)
     if s == "knorm_rerotate":
         n_kept = O.kept_count(K.shape[2], ratio)
         return O.key_rerotation_compress(O.knorm_scores(K), K, V, n_kept, extra["inv_freq"])[:2]
@@ -252,7 +262,7 @@ def cpu_leg(w: dict, budget_s: float, max_reps: int = 3):
     torch.set_num_threads(os.cpu_count() or 1)
     ratio = effective_ratio(w)
     # rough cost model (ms per 1k tokens on ~8 cores) to size the sample without trial runs
-    per_k = {"knorm": 3.5, "knorm_rerotate": 6.0, "adakv_ea": 50.0, "streaming": 3.0, "snapkv": 16.0, "expected_attention": 50.0}[w["scorer"]]
+    per_k = {"knorm": 3.5, "keydiff": 8.0, "knorm_rerotate": 6.0, "adakv_ea": 50.0, "streaming": 3.0, "snapkv": 16.0, "expected_attention": 50.0}[w["scorer"]]
     S = w["S"]
     while S > 4096 and per_k * S / 1000 / 1000 * max_reps > budget_s:
         S //= 2
@@ -395,7 +405,7 @@ def main():
     elif w["scorer"] == "adakv_ea":  # EA score (memset, logits, vnorm, finalize, sentinel) + 2 x kvp_scores_select (3 each)
         launches = 5 + 2 * native.launches_per_compress(p, 0)
     else:
-        scorer_id = {"knorm": 1, "streaming": 2, "snapkv": 3, "expected_attention": 4}[w["scorer"]]
+        scorer_id = {"knorm": 1, "streaming": 2, "snapkv": 3, "expected_attention": 4, "keydiff": 5}[w["scorer"]]
         launches = native.launches_per_compress(p, scorer_id)
     roofline = {
         "bound": "hbm", "kernel": f"kvp_{w['scorer']}_compress ({launches} launches: score, select, compact)",

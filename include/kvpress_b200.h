@@ -12,6 +12,7 @@
  *     kvp_streaming_*          <- kvpress/presses/streaming_llm_press.py:38-54
  *     kvp_snapkv_*             <- kvpress/presses/snapkv_press.py:41-105
  *     kvp_expected_attention_* <- kvpress/presses/expected_attention_press.py:126-165
+ *     kvp_keydiff_*            <- kvpress/presses/keydiff_press.py:36-46
  *     kvp_scores_compress      <- scorer_press.py:93-100 for an arbitrary score tensor
  *                                 (what wrapper presses / user ScorerPress subclasses need)
  *
@@ -65,7 +66,8 @@ typedef enum kvp_scorer {
     KVP_SCORER_KNORM = 1,
     KVP_SCORER_STREAMING = 2,
     KVP_SCORER_SNAPKV = 3,
-    KVP_SCORER_EXPECTED_ATTENTION = 4
+    KVP_SCORER_EXPECTED_ATTENTION = 4,
+    KVP_SCORER_KEYDIFF = 5
 } kvp_scorer;
 
 /* One ScorerPress.compress call on one layer's cache. */
@@ -143,6 +145,14 @@ int kvp_scores_compress(const kvp_problem* p, const void* scores, const int64_t*
                         const void* K, const void* V, void* K_out, void* V_out,
                         int32_t* idx_out, void* workspace, size_t workspace_bytes,
                         kvp_stream_t stream);
+
+/* ---- KeyDiffPress (kvpress/presses/keydiff_press.py:36-46): score = -cos(k, anchor), anchor = mean over
+ * positions of k / ||k||; fp32 evaluation, one rounding to the K dtype. Two streaming passes over K. */
+int kvp_keydiff_score(const kvp_problem* p, const void* K, void* scores_out, void* workspace,
+                      size_t workspace_bytes, kvp_stream_t stream);
+int kvp_keydiff_compress(const kvp_problem* p, const void* K, const void* V, void* K_out, void* V_out,
+                         int32_t* idx_out, void* scores_out, void* workspace, size_t workspace_bytes,
+                         kvp_stream_t stream);
 
 /* ---- selection only: the n_kept best positions of every [S] score row, ascending, into idx_out
  * [B, Hkv, n_kept]; no K/V are touched (p->D and the K/V strides are ignored). What head-wise presses need:

@@ -11,6 +11,7 @@ from kvpress_b200.presses.compression_ratio_decoding_press import CompressionRat
 from kvpress_b200.presses.decoding_press import DecodingPress
 from kvpress_b200.presses.expected_attention_press import ExpectedAttentionPress
 from kvpress_b200.presses.key_rerotation_press import KeyRerotationPress
+from kvpress_b200.presses.keydiff_press import KeyDiffPress
 from kvpress_b200.presses.knorm_press import KnormPress
 from kvpress_b200.presses.per_layer_compression_press import PerLayerCompressionPress
 from kvpress_b200.presses.prefill_decoding_press import PrefillDecodingPress
@@ -29,6 +30,7 @@ __all__ = [
     "StreamingLLMPress",
     "DecodingPress",
     "KeyRerotationPress",
+    "KeyDiffPress",
     "AdaKVPress",
     "ChunkPress",
     "ComposedPress",

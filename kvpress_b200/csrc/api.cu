@@ -75,6 +75,7 @@ static WsLayout layout(const Dims& d, int scorer, int window) {
     L.scorer_bytes = 0;
     if (scorer == KVP_SCORER_SNAPKV) L.scorer_bytes = snapkv_scratch_bytes(d, window);
     if (scorer == KVP_SCORER_EXPECTED_ATTENTION) L.scorer_bytes = ea_scratch_bytes(d);
+    if (scorer == KVP_SCORER_KEYDIFF) L.scorer_bytes = keydiff_scratch_bytes(d);
     off = align_up(off + L.scorer_bytes, 256);
     L.total = off;
     return L;
@@ -152,6 +153,7 @@ int kvp_launches_per_compress(const kvp_problem* p, int scorer, int* launches_ou
         case KVP_SCORER_KNORM:  // memset + (fused | score, select+compact)
             *launches_out = ((size_t)p->B * p->Hkv * p->S * p->D * 2 <= ((size_t)32 << 20)) ? 2 : 3;
             break;
+        case KVP_SCORER_KEYDIFF: *launches_out = 5; break;  // memset, anchor partials, merge, score, select+compact
         case KVP_SCORER_SNAPKV: *launches_out = 6; break;  // memset, stats, memset, colsum, finalize, select+compact
         case KVP_SCORER_EXPECTED_ATTENTION: *launches_out = 5; break;  // memset, logits, vnorm (side stream), finalize, select+compact
         default: return KVP_ERR_BAD_ARGUMENT;
@@ -202,6 +204,42 @@ int kvp_knorm_compress(const kvp_problem* p, const void* K, const void* V, void*
         if (e != cudaErrorNotSupported) return e == cudaSuccess ? KVP_OK : fail_cuda(e);
     }
     e = launch_knorm_score(d, p->dtype, K, ws, scores_out, true, st);
+    if (e != cudaSuccess) return fail_cuda(e);
+    return select_and_compact(d, K, V, K_out, V_out, idx_out, ws, st);
+}
+
+// ---- KeyDiff -------------------------------------------------------------------------------------
+int kvp_keydiff_score(const kvp_problem* p, const void* K, void* scores_out, void* workspace,
+                      size_t workspace_bytes, kvp_stream_t stream) {
+    Dims d;
+    int rc = validate(p, &d);
+    if (rc) return rc;
+    if (!K || !scores_out) return KVP_ERR_NULL_POINTER;
+    if (!aligned16(K)) return KVP_ERR_BAD_STRIDE;
+    Workspace ws;
+    WsLayout L;
+    if ((rc = carve(d, KVP_SCORER_KEYDIFF, 0, workspace, workspace_bytes, &ws, &L))) return rc;
+    cudaError_t e = launch_keydiff_score(d, p->dtype, K, ws, scores_out, false, static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorNotSupported) return KVP_ERR_UNSUPPORTED_SHAPE;
+    return e == cudaSuccess ? KVP_OK : fail_cuda(e);
+}
+
+int kvp_keydiff_compress(const kvp_problem* p, const void* K, const void* V, void* K_out, void* V_out,
+                         int32_t* idx_out, void* scores_out, void* workspace, size_t workspace_bytes,
+                         kvp_stream_t stream) {
+    Dims d;
+    int rc = validate(p, &d);
+    if (rc) return rc;
+    if (d.n_kept == 0) return KVP_OK;
+    if ((rc = check_io(K, V, K_out, V_out))) return rc;
+    Workspace ws;
+    WsLayout L;
+    if ((rc = carve(d, KVP_SCORER_KEYDIFF, 0, workspace, workspace_bytes, &ws, &L))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(ws.hist_hi, 0, L.hist_bytes, st);
+    if (e != cudaSuccess) return fail_cuda(e);
+    e = launch_keydiff_score(d, p->dtype, K, ws, scores_out, true, st);
+    if (e == cudaErrorNotSupported) return KVP_ERR_UNSUPPORTED_SHAPE;
     if (e != cudaSuccess) return fail_cuda(e);
     return select_and_compact(d, K, V, K_out, V_out, idx_out, ws, st);
 }

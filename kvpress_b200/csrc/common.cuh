@@ -246,6 +246,9 @@ size_t snapkv_scratch_bytes(const Dims& d, int window);
 cudaError_t launch_snapkv_score(const Dims& d, int dtype, const void* K, const void* q_window,
                                 int window, int kernel_size, const Workspace& ws,
                                 void* scores_out, bool want_keys, cudaStream_t st);
+size_t keydiff_scratch_bytes(const Dims& d);
+cudaError_t launch_keydiff_score(const Dims& d, int dtype, const void* K, const Workspace& ws,
+                                 void* scores_out, bool want_keys, cudaStream_t st);
 size_t ea_scratch_bytes(const Dims& d);
 cudaError_t launch_fill_sentinel(int dtype, void* scores_out, int R, int S, int lo, int hi,
                                  const Workspace& ws, cudaStream_t st);

@@ -47,6 +47,8 @@ def _require_pinned(name: str, t: torch.Tensor):
 def _run_chunk(scorer: str, k, v, n_kept: int, b: int, hq0: int, hq1: int, params: dict):
     if scorer == "knorm":
         return native.knorm_compress(k, v, n_kept, _pinned_values=not v.is_cuda)[:2]
+    if scorer == "keydiff":
+        return native.keydiff_compress(k, v, n_kept, _pinned_values=not v.is_cuda)[:2]
     if scorer == "streaming":
         return native.streaming_compress(k, v, n_kept, params.get("n_sink", 4), _pinned_kv=not v.is_cuda)[:2]
     if scorer == "snapkv":
@@ -67,7 +69,7 @@ def compress_host(scorer: str, keys_host: torch.Tensor, values_host: torch.Tenso
                   **params):
     """ScorerPress.compress (scorer_press.py:76-102) for a cache held in pinned host memory.
 
-    scorer: "knorm" | "streaming" | "snapkv" | "expected_attention"; params are the scorer's device-resident
+    scorer: "knorm" | "keydiff" | "streaming" | "snapkv" | "expected_attention"; params are the scorer's device-resident
     small operands (q_window / mu, cov, ...) with all Hq heads — they are sliced per chunk here.
     Returns pinned host (K', V') of shape [B, Hkv, n_kept, D], rows in ascending position order. The call
     returns after the three streams have drained (outputs are ready to read on the host)."""

@@ -17,7 +17,7 @@ import torch
 _LIB_NAME = "libkvpress_b200.so"
 _LIB_PATH = Path(__file__).resolve().parent / _LIB_NAME
 
-SCORER_GENERIC, SCORER_KNORM, SCORER_STREAMING, SCORER_SNAPKV, SCORER_EXPECTED_ATTENTION = range(5)
+SCORER_GENERIC, SCORER_KNORM, SCORER_STREAMING, SCORER_SNAPKV, SCORER_EXPECTED_ATTENTION, SCORER_KEYDIFF = range(6)
 _DTYPES = {torch.bfloat16: 0, torch.float16: 1}
 
 
@@ -65,6 +65,8 @@ SIGNATURES = {
         ctypes.c_int, [_PP, _P, _P, _P, _P, ctypes.c_float, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "kvp_scores_compress": (
         ctypes.c_int, [_PP, _P, ctypes.POINTER(ctypes.c_int64), _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "kvp_keydiff_score": (ctypes.c_int, [_PP, _P, _P, _P, _SZ, _P]),
+    "kvp_keydiff_compress": (ctypes.c_int, [_PP, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "kvp_scores_select": (ctypes.c_int, [_PP, _P, ctypes.POINTER(ctypes.c_int64), _P, _P, _SZ, _P]),
     "kvp_scores_compress_rerotate": (
         ctypes.c_int, [_PP, _P, ctypes.POINTER(ctypes.c_int64), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
@@ -231,6 +233,39 @@ def knorm_compress(keys, values, n_kept: int, return_indices: bool = False, retu
                     ctypes.byref(p), _ptr(keys), _ptr(values), _ptr(k_out), _ptr(v_out), _ptr(idx), _ptr(scores),
                     _ptr(ws), ws.numel(), _stream()),
                 "kvp_knorm_compress",
+            )
+    return k_out, v_out, idx, scores
+
+
+# --------------------------------------------------------------------------------------------------
+# KeyDiff
+# --------------------------------------------------------------------------------------------------
+def keydiff_score(keys: torch.Tensor) -> torch.Tensor:
+    _require_cuda_kv(keys, keys)
+    keys = _normalise(keys)
+    p = make_problem(keys, keys, 0)
+    scores = torch.empty(keys.shape[:3], dtype=keys.dtype, device=keys.device)
+    with torch.cuda.device(keys.device):
+        ws = _workspace(p, SCORER_KEYDIFF, keys.device)
+        _check(load().kvp_keydiff_score(ctypes.byref(p), _ptr(keys), _ptr(scores), _ptr(ws), ws.numel(), _stream()),
+               "kvp_keydiff_score")
+    return scores
+
+
+def keydiff_compress(keys, values, n_kept: int, return_indices: bool = False, return_scores: bool = False,
+                     _pinned_values: bool = False):
+    _require_cuda_kv(keys, values, pinned_values=_pinned_values)
+    keys, values = _normalise(keys), _normalise(values)
+    p = make_problem(keys, values, n_kept)
+    k_out, v_out, idx, scores = _alloc_out(keys, n_kept, return_indices, return_scores)
+    if n_kept > 0:
+        with torch.cuda.device(keys.device):
+            ws = _workspace(p, SCORER_KEYDIFF, keys.device)
+            _check(
+                load().kvp_keydiff_compress(
+                    ctypes.byref(p), _ptr(keys), _ptr(values), _ptr(k_out), _ptr(v_out), _ptr(idx), _ptr(scores),
+                    _ptr(ws), ws.numel(), _stream()),
+                "kvp_keydiff_compress",
             )
     return k_out, v_out, idx, scores
 

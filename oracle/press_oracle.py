@@ -252,6 +252,25 @@ def expected_attention_scores_fp32(keys, values, mu, cov, epsilon: float, n_sink
 
 
 # --------------------------------------------------------------------------------------------------
+# keydiff_press.py:36-46
+# --------------------------------------------------------------------------------------------------
+def keydiff_scores(keys: torch.Tensor) -> torch.Tensor:
+    """keydiff_press.py:45-46 — the reference's two ATen calls; every op rounds to the key dtype."""
+    anchor = F.normalize(keys, p=2, dim=-1).mean(dim=2, keepdim=True)
+    return -F.cosine_similarity(keys, anchor, dim=-1)
+
+
+def keydiff_scores_fp32(keys: torch.Tensor) -> torch.Tensor:
+    """fp32 evaluation of the same formula from the 16-bit keys (what the kernel rounds once):
+    anchor = mean_s k/max(||k||,1e-12);  score = -(k.anchor)/(max(||k||,1e-8) max(||anchor||,1e-8))."""
+    k = keys.float()
+    kn = k.norm(dim=-1, keepdim=True)
+    anchor = (k / kn.clamp_min(1e-12)).mean(dim=2, keepdim=True)
+    an = anchor.norm(dim=-1, keepdim=True).clamp_min(1e-8)
+    return -((k * anchor).sum(-1) / kn.squeeze(-1).clamp_min(1e-8) / an.squeeze(-1))
+
+
+# --------------------------------------------------------------------------------------------------
 # key_rerotation_press.py:50-152 (SURVEY §8f "next" row 1)
 # --------------------------------------------------------------------------------------------------
 def rerotate_cos_sin(dtype, inv_freq: torch.Tensor, selected_positions: torch.Tensor):

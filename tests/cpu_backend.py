@@ -67,12 +67,20 @@ def scores_compress_rerotate(scores, keys, values, n_kept, inv_freq, return_indi
     return k_out, O.gather_rows(values, idx), (idx.to(torch.int32) if return_indices else None)
 
 
+def keydiff_score(keys):
+    return O.keydiff_scores(keys)
+
+
+def keydiff_compress(keys, values, n_kept, return_indices=False, return_scores=False):
+    return _select(O.keydiff_scores(keys), keys, values, n_kept, return_indices, return_scores)
+
+
 def scores_select(scores, n_kept):
     return O.select_lowest_index_ties(scores, n_kept).to(torch.int32)
 
 
 PATCHED = ["knorm_score", "knorm_compress", "streaming_score", "streaming_compress", "snapkv_score",
-           "snapkv_compress", "expected_attention_score", "expected_attention_compress", "scores_compress", "scores_compress_rerotate", "scores_select"]
+           "snapkv_compress", "expected_attention_score", "expected_attention_compress", "scores_compress", "scores_compress_rerotate", "scores_select", "keydiff_score", "keydiff_compress"]
 
 
 def install(monkeypatch):

@@ -176,7 +176,30 @@ def make_rerotation():
     print("rerotation", out["cases"].tolist())
 
 
+def make_keydiff():
+    """keydiff_press.py:36-46 run unmodified: scores for three seeded caches (incl. a zero key and duplicates)."""
+    kvpress = import_reference()
+    out = {}
+    cases = [("a", 2, 2, 384, 64, torch.bfloat16), ("b", 1, 2, 1000, 128, torch.bfloat16), ("c", 1, 2, 300, 64, torch.float16)]
+    out["cases"] = np.array([[B, H, S, D, int(dt == torch.float16)] for _, B, H, S, D, dt in cases], dtype=np.int64)
+    for tag, B, H, S, D, dtype in cases:
+        torch.manual_seed(200 + S)
+        keys = (torch.randn(B, H, S, D) + 0.5 * torch.randn(B, H, 1, D)).to(dtype)   # a common direction + noise
+        if dtype == torch.bfloat16:
+            # (in fp16 the reference's eps=1e-12 underflows to 0 and a zero key turns every score into NaN)
+            keys[:, :, 7] = 0
+        keys[:, :, 20:24] = keys[:, :, 10:14]
+        with torch.no_grad():
+            sc = kvpress.KeyDiffPress().score(None, None, keys, None, None, {})
+        out[f"{tag}_keys"], out[f"{tag}_scores"] = u16(keys), u16(sc)
+    np.savez_compressed(OUT / "keydiff.npz", **out)
+    print("keydiff", out["cases"].tolist())
+
+
 if __name__ == "__main__":
+    if "--keydiff-only" in sys.argv:
+        make_keydiff()
+        sys.exit(0)
     if "--rerotation-only" in sys.argv:
         make_rerotation()
         sys.exit(0)
@@ -186,3 +209,4 @@ if __name__ == "__main__":
     make_case("half64", B=1, Hq=2, Hkv=2, D=64, hidden=128, S=300, seed=14, dtype=torch.float16)
     make_decoding_table()
     make_rerotation()
+    make_keydiff()

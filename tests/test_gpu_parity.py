@@ -646,3 +646,83 @@ def test_adakv_selection_at_128k():
     # every pruned score <= every kept, unprotected score
     boosted = scores.float().scatter(-1, safe, float("inf"))
     assert boosted[pruned].max().item() <= boosted[~pruned].min().item()
+
+
+# ---------------------------------------------------------------------------------------------------
+# KeyDiffPress
+# ---------------------------------------------------------------------------------------------------
+def _assert_keydiff_scores(got: torch.Tensor, keys_cpu: torch.Tensor, ref16=None):
+    """Kernel score == fp32 evaluation of the reference formula rounded once (<= 1 ulp; absolute 2^-9 around the
+    sign change where ulps shrink to nothing); within 8 ulp of the reference's own 16-bit scores."""
+    got = got.cpu()
+    hi = O.keydiff_scores_fp32(keys_cpu)
+    want = hi.to(got.dtype)
+    small = hi.abs() < 2.0 ** -5
+    assert ulp16_diff(got, want)[~small].max().item() <= 1
+    assert (got.float() - hi)[small].abs().max().item() <= 2.0 ** -9 if small.any() else True
+    if ref16 is not None:
+        d = ulp16_diff(got, ref16)[~small]
+        assert d.max().item() <= 8 and (d <= 2).float().mean().item() > 0.97
+
+
+def test_keydiff_vs_golden():
+    import numpy as np
+
+    from tests.conftest import GOLDEN_DIR
+    nat = _native()
+    z = np.load(GOLDEN_DIR / "keydiff.npz")
+    for tag, (B, H, S, D, is_half) in zip("abc", z["cases"]):
+        dtype = torch.float16 if is_half else torch.bfloat16
+        keys = torch.from_numpy(z[f"{tag}_keys"].copy()).view(dtype)
+        ref = torch.from_numpy(z[f"{tag}_scores"].copy()).view(dtype)
+        sc = nat.keydiff_score(keys.to(DEV))
+        _assert_keydiff_scores(sc, keys, ref)
+        values = torch.randn(keys.shape).to(dtype)
+        for ratio in (0.25, 0.6):
+            n_kept = O.kept_count(int(S), ratio)
+            k2, v2, idx, sc2 = nat.keydiff_compress(keys.to(DEV), values.to(DEV), n_kept, return_indices=True,
+                                                    return_scores=True)
+            assert torch.equal(sc2, sc)
+            assert torch.equal(idx.long().cpu(), O.select_lowest_index_ties(sc.cpu(), n_kept))
+            _check_compaction(keys, values, k2, v2, idx)
+            assert O.check_selection(ref, idx.long().cpu(), n_kept, ulp_slack=8)["ok"]
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 32768, 128), (2, 3, 5000, 64), (1, 2, 1023, 256), (3, 1, 257, 32)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_keydiff_vs_fp32_oracle_random(shape, dtype):
+    nat = _native()
+    B, H, S, D = shape
+    g = torch.Generator().manual_seed(S + D)
+    keys = (torch.randn(shape, generator=g) + 0.7 * torch.randn(B, H, 1, D, generator=g)).to(dtype)
+    values = torch.randn(shape, generator=g).to(dtype)
+    # a strided view (every other head of a wider cache) must be consumed in place
+    wide = torch.zeros(B, 2 * H, S, D, dtype=dtype, device=DEV)
+    wide[:, ::2] = keys.to(DEV)
+    sc = nat.keydiff_score(wide[:, ::2])
+    _assert_keydiff_scores(sc, keys)
+    n_kept = O.kept_count(S, 0.5)
+    k2, v2, idx, _ = nat.keydiff_compress(wide[:, ::2], values.to(DEV), n_kept, return_indices=True)
+    assert torch.equal(idx.long().cpu(), O.select_lowest_index_ties(sc.cpu(), n_kept))
+    _check_compaction(keys, values, k2, v2, idx)
+
+
+def test_keydiff_128k_properties():
+    nat = _native()
+    B, H, S, D = 1, 8, 131072, 128
+    g = torch.Generator(device=DEV).manual_seed(9)
+    k = (torch.randn(B, H, S, D, generator=g, device=DEV) + torch.randn(B, H, 1, D, generator=g, device=DEV)).to(torch.bfloat16)
+    v = torch.randn(B, H, S, D, generator=g, device=DEV).to(torch.bfloat16)
+    n_kept = O.kept_count(S, 0.5)
+    k_out, v_out, idx, scores = nat.keydiff_compress(k, v, n_kept, return_indices=True, return_scores=True)
+    assert torch.equal(k_out, _gather_dev(k, idx)) and torch.equal(v_out, _gather_dev(v, idx))
+    _assert_topk_of_own_scores(scores, idx, n_kept, slice(0, 0))
+    # device-side fp32 evaluation of the formula
+    kf = k.float()
+    kn = kf.norm(dim=-1, keepdim=True)
+    anchor = (kf / kn.clamp_min(1e-12)).mean(dim=2, keepdim=True)
+    hi = -((kf * anchor).sum(-1) / kn.squeeze(-1).clamp_min(1e-8) / anchor.norm(dim=-1).clamp_min(1e-8))
+    assert (scores.float() - hi).abs().max().item() <= 2.0 ** -8
+    # determinism: the anchor reduction has a fixed order
+    again = nat.keydiff_score(k)
+    assert torch.equal(again, scores)

@@ -131,3 +131,26 @@ def test_rerotation_matches_reference_bit_exact():
             kn_idx = get(f"knorm_idx_{i}").long()
             k3 = O.rerotate_keys(keys, kn_idx, inv_freq)
             assert torch.equal(k3.view(torch.int16), get(f"knorm_k_{i}").view(torch.int16)), (tag, r)
+
+
+# ---- KeyDiffPress --------------------------------------------------------------------
+def _keydiff_cases():
+    z = np.load(GOLDEN_DIR / "keydiff.npz")
+    for tag, (B, H, S, D, is_half) in zip("abc", z["cases"]):
+        dtype = torch.float16 if is_half else torch.bfloat16
+        yield (tag, torch.from_numpy(z[f"{tag}_keys"].copy()).view(dtype),
+               torch.from_numpy(z[f"{tag}_scores"].copy()).view(dtype))
+
+
+def test_keydiff_oracle_matches_reference_and_its_fp32_form():
+    for tag, keys, ref_scores in _keydiff_cases():
+        got = O.keydiff_scores(keys)
+        assert torch.equal(got.view(torch.int16), ref_scores.view(torch.int16)), tag
+        # the fp32 evaluation (what the kernel rounds once) stays within a few 16-bit ulps of the reference,
+        # which rounds after each of its ~6 ATen ops
+        hi = O.keydiff_scores_fp32(keys).to(keys.dtype)
+        d = ulp16_diff(hi, ref_scores)
+        near_zero = ref_scores.float().abs() < 2.0 ** -6      # ulps are meaningless around a sign change
+        assert d[~near_zero].max().item() <= 8 and (d[~near_zero] <= 2).float().mean().item() > 0.97, tag
+        if near_zero.any():
+            assert (hi.float() - ref_scores.float()).abs()[near_zero].max().item() < 2.0 ** -8

@@ -9,7 +9,7 @@ import pytest
 import torch
 from transformers import DynamicCache
 
-from kvpress_b200 import ExpectedAttentionPress, KnormPress, SnapKVPress, StreamingLLMPress
+from kvpress_b200 import ExpectedAttentionPress, KeyDiffPress, KnormPress, SnapKVPress, StreamingLLMPress
 from tests import cpu_backend
 from tests.tiny_models import tiny_llama, tiny_qwen3
 
@@ -40,6 +40,7 @@ CASES = [
     ("streaming", lambda m: m.StreamingLLMPress, StreamingLLMPress, {"n_sink": 4}),
     ("snapkv", lambda m: m.SnapKVPress, SnapKVPress, {"window_size": 16, "kernel_size": 5}),
     ("expected_attention", lambda m: m.ExpectedAttentionPress, ExpectedAttentionPress, {"n_sink": 4}),
+    ("keydiff", lambda m: m.KeyDiffPress, KeyDiffPress, {}),
 ]
 
 
