@@ -110,27 +110,41 @@ keydiff_anchor_kernel(const T* __restrict__ K, Strides3 ks, int H, int S, int D,
 }
 
 // ---- merge: anchor = (sum of partials) / S, ||anchor|| --------------------------------------------
-__global__ void __launch_bounds__(256)
+// One CTA of 1024 threads per row: G = 1024 / D_pad thread groups, group g sums the chunks c = g, g+G, ... in
+// a fixed order (4 chains), the groups meet in shared memory in a fixed order -> deterministic, and the serial
+// chain per thread is n_chunks / G long instead of n_chunks (26 us -> a few us at 128k).
+constexpr int kKdMergeThreads = 1024;
+__global__ void __launch_bounds__(kKdMergeThreads)
 keydiff_merge_kernel(int S, int D, int n_chunks, KeyDiffScratch sc) {
+    __shared__ float s_grp[kKdMergeThreads];
     __shared__ float s_sq[256];
     const int row = blockIdx.x, tid = threadIdx.x;
+    const int d_pad = (D <= 32) ? 32 : (D <= 64) ? 64 : (D <= 128) ? 128 : 256;
+    const int G = kKdMergeThreads / d_pad;
+    const int g = tid / d_pad, dd = tid % d_pad;
+    float t = 0.f;
+    if (dd < D) {
+        const float* p = sc.partial + (size_t)row * n_chunks * D + dd;
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+        int c = g;
+        for (; c + 3 * G < n_chunks; c += 4 * G) {
+            t0 += p[(size_t)c * D];
+            t1 += p[(size_t)(c + G) * D];
+            t2 += p[(size_t)(c + 2 * G) * D];
+            t3 += p[(size_t)(c + 3 * G) * D];
+        }
+        for (; c < n_chunks; c += G) t0 += p[(size_t)c * D];
+        t = (t0 + t1) + (t2 + t3);
+    }
+    s_grp[tid] = t;
+    __syncthreads();
     float a = 0.f;
     if (tid < D) {
-        const float* p = sc.partial + (size_t)row * n_chunks * D + tid;
-        // four independent chains, fixed order: deterministic and latency-tolerant
-        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-        int c = 0;
-        for (; c + 4 <= n_chunks; c += 4) {
-            t0 += p[(size_t)c * D];
-            t1 += p[(size_t)(c + 1) * D];
-            t2 += p[(size_t)(c + 2) * D];
-            t3 += p[(size_t)(c + 3) * D];
-        }
-        for (; c < n_chunks; ++c) t0 += p[(size_t)c * D];
-        a = ((t0 + t1) + (t2 + t3)) / (float)S;
+        for (int gg = 0; gg < G; ++gg) a += s_grp[gg * d_pad + tid];
+        a /= (float)S;
         sc.anchor[(size_t)row * D + tid] = a;
     }
-    s_sq[tid] = a * a;
+    if (tid < 256) s_sq[tid] = a * a;
     __syncthreads();
     for (int off = 128; off >= 1; off >>= 1) {
         if (tid < off) s_sq[tid] += s_sq[tid + off];
@@ -228,7 +242,7 @@ static cudaError_t launch_keydiff_t(const Dims& d, const void* K, const Workspac
     else KVP_KD_ANCHOR(32);
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) return e;
-    keydiff_merge_kernel<<<d.R, 256, 0, st>>>(d.S, d.D, n_chunks, sc);
+    keydiff_merge_kernel<<<d.R, kKdMergeThreads, 0, st>>>(d.S, d.D, n_chunks, sc);
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return e;
     if (nvec <= 4) KVP_KD_SCORE(4);
     else if (nvec <= 8) KVP_KD_SCORE(8);
