@@ -54,3 +54,64 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setenv("KVPRESS_B200_LIB", str(tmp_path / "nope.so"))
     with pytest.raises(native.NativeLibraryError, match="no CPU or PyTorch fallback"):
         native.load()
+
+
+def test_argument_validation_of_every_compress_entry_point_without_gpu():
+    """Error behaviour of the C ABI (include/kvpress_b200.h "Return value"): every check below fails before the first
+    CUDA call, so it runs on the GPU-less build box. Pointers are fake, aligned, never dereferenced."""
+    lib = native.load()
+    P = ctypes.c_void_p
+    good, odd = P(0x10000), P(0x10008 + 4)          # 16-byte aligned / misaligned
+    stream = P(0)
+
+    def problem(**kw):
+        p = native.KvpProblem()
+        p.B, p.Hkv, p.Hq, p.S, p.D, p.n_kept, p.dtype = 1, 2, 2, 1000, 128, 500, 0
+        p.k_stride = (ctypes.c_int64 * 3)(2 * 1000 * 128, 1000 * 128, 128)
+        p.v_stride = (ctypes.c_int64 * 3)(2 * 1000 * 128, 1000 * 128, 128)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    sstride = (ctypes.c_int64 * 2)(2000, 1000)
+    calls = {
+        "knorm": lambda p, K, ws, n: lib.kvp_knorm_compress(ctypes.byref(p), K, good, good, good, None, None, ws, n, stream),
+        "keydiff": lambda p, K, ws, n: lib.kvp_keydiff_compress(ctypes.byref(p), K, good, good, good, None, None, ws, n, stream),
+        "snapkv": lambda p, K, ws, n: lib.kvp_snapkv_compress(ctypes.byref(p), K, good, good, 64, 5, good, good, None, None, ws, n, stream),
+        "expected_attention": lambda p, K, ws, n: lib.kvp_expected_attention_compress(
+            ctypes.byref(p), K, good, good, good, 0.0, 4, 1, good, good, None, None, ws, n, stream),
+        "generic": lambda p, K, ws, n: lib.kvp_scores_compress(ctypes.byref(p), good, sstride, K, good, good, good, None, ws, n, stream),
+        "rerotate": lambda p, K, ws, n: lib.kvp_scores_compress_rerotate(
+            ctypes.byref(p), good, sstride, K, good, ctypes.cast(good, ctypes.POINTER(ctypes.c_float)), good, good, None, ws, n, stream),
+    }
+    for name, call in calls.items():
+        assert call(problem(), P(0), good, 1 << 30) == -1, name                  # NULL K
+        assert call(problem(), odd, good, 1 << 30) == -4, name                   # misaligned K
+        assert call(problem(n_kept=1001), good, good, 1 << 30) == -7, name        # n_kept > S
+        assert call(problem(D=12), good, good, 1 << 30) == -2, name               # head_dim not a multiple of 8
+        assert call(problem(dtype=3), good, good, 1 << 30) == -3, name            # unknown dtype
+        bad = problem()
+        bad.k_stride = (ctypes.c_int64 * 3)(2 * 1000 * 128, 1000 * 128, 100)     # rows overlap
+        assert call(bad, good, good, 1 << 30) == -4, name
+        assert call(problem(), good, good, 64) == -5, name                        # workspace too small
+        assert call(problem(), good, P(0), 1 << 30) == -1, name                   # NULL workspace
+        assert call(problem(n_kept=0), good, good, 1 << 30) == 0, name            # nothing to keep: no work, OK
+    # streaming has no workspace; selection-only has no K/V
+    p = problem()
+    assert lib.kvp_streaming_compress(ctypes.byref(p), 4, P(0), good, good, good, None, stream) == -1
+    assert lib.kvp_scores_select(ctypes.byref(p), P(0), sstride, ctypes.cast(good, ctypes.POINTER(ctypes.c_int32)), good,
+                                 1 << 30, stream) == -1
+    assert lib.kvp_scores_select(ctypes.byref(p), good, sstride, None, good, 1 << 30, stream) == -1
+    assert lib.kvp_scores_select(ctypes.byref(p), good, sstride, ctypes.cast(good, ctypes.POINTER(ctypes.c_int32)), good,
+                                 64, stream) == -5
+    # workspace sizing is monotone in S and covers every scorer id
+    sizes = []
+    for scorer in range(6):
+        out = ctypes.c_size_t(0)
+        assert lib.kvp_workspace_bytes(ctypes.byref(problem()), scorer, ctypes.byref(out)) == 0
+        big = ctypes.c_size_t(0)
+        assert lib.kvp_workspace_bytes(ctypes.byref(problem(S=4000, n_kept=500)), scorer, ctypes.byref(big)) == 0
+        assert big.value > out.value > 0
+        sizes.append(out.value)
+    n = ctypes.c_int(0)
+    assert lib.kvp_launches_per_compress(ctypes.byref(problem()), 99, ctypes.byref(n)) == -7
