@@ -5,7 +5,9 @@ CUDA behind the reference's own press API (BasePress / ScorerPress hooks and the
 from kvpress_b200.pipeline import KVPressTextGenerationPipeline
 from kvpress_b200.presses.adakv_press import AdaKVPress
 from kvpress_b200.presses.base_press import SUPPORTED_MODELS, BasePress
+from kvpress_b200.presses.block_press import BlockPress
 from kvpress_b200.presses.chunk_press import ChunkPress
+from kvpress_b200.presses.chunkkv_press import ChunkKVPress
 from kvpress_b200.presses.composed_press import ComposedPress
 from kvpress_b200.presses.compression_ratio_decoding_press import CompressionRatioDecodingPress
 from kvpress_b200.presses.decoding_press import DecodingPress
@@ -32,7 +34,9 @@ __all__ = [
     "KeyRerotationPress",
     "KeyDiffPress",
     "AdaKVPress",
+    "BlockPress",
     "ChunkPress",
+    "ChunkKVPress",
     "ComposedPress",
     "PerLayerCompressionPress",
     "PrefillDecodingPress",

@@ -248,3 +248,48 @@ def test_adakv_masks_the_same_keys_as_reference(monkeypatch, ref, inner, alpha):
         assert a == b
     assert c_our.get_seq_length() == c_ref.get_seq_length() == S + 1      # AdaKV never shrinks the cache
     assert torch.allclose(y_our, y_ref, atol=1e-5)
+
+
+@pytest.mark.parametrize("inner", ["knorm", "snapkv", "expected_attention"])
+@pytest.mark.parametrize("n_tokens,chunk", [(160, 20), (150, 20), (150, 32), (15, 20)])
+def test_chunkkv_press_same_rows_as_reference(monkeypatch, ref, inner, n_tokens, chunk):
+    """chunkkv_press.py:52-117: whole chunks kept, ranked by head-summed mean score; ragged tail; S < chunk."""
+    from kvpress_b200 import ChunkKVPress
+
+    if inner != "knorm" and n_tokens < 32:
+        pytest.skip("window scorers need more tokens than their window")
+    cpu_backend.install(monkeypatch)
+    model = tiny_llama()
+    ids = _distinct_ids(31, n=n_tokens)
+    _, ref_cls, our_cls, kw = next(c for c in CASES if c[0] == inner)
+    if inner == "snapkv":
+        kw = {"window_size": 8, "kernel_size": 3}
+    theirs, ours = _prefill_both(ref.ChunkKVPress(ref_cls(ref)(compression_ratio=0.4, **kw), chunk_length=chunk),
+                                 ChunkKVPress(our_cls(compression_ratio=0.4, **kw), chunk_length=chunk), model, ids)
+    assert ours.get_seq_length() == theirs.get_seq_length()
+    if n_tokens < chunk:                               # plain press.compress: same rows, reference in top-k order
+        _assert_same_rows(ours, theirs)
+        return
+    for lo, lt in zip(ours.layers, theirs.layers):     # both emit position order: caches are equal row by row
+        assert torch.equal(lo.keys, lt.keys) and torch.equal(lo.values, lt.values)
+
+
+@pytest.mark.parametrize("inner", ["knorm", "keydiff"])
+@pytest.mark.parametrize("block_size", [16, 50, 400])
+def test_block_press_same_rows_as_reference(monkeypatch, ref, inner, block_size):
+    """block_press.py:49-98 incl. the reference's own invariant (tests/presses/test_block_press.py:30-63):
+    a block at least as long as the context is the plain press."""
+    from kvpress_b200 import BlockPress
+
+    cpu_backend.install(monkeypatch)
+    model = tiny_llama()
+    ids = _distinct_ids(32)
+    _, ref_cls, our_cls, kw = next(c for c in CASES if c[0] == inner)
+    theirs, ours = _prefill_both(ref.BlockPress(ref_cls(ref)(compression_ratio=0.5, **kw), block_size=block_size),
+                                 BlockPress(our_cls(compression_ratio=0.5, **kw), block_size=block_size), model, ids)
+    _assert_same_rows(ours, theirs)
+    if block_size >= ids.shape[1]:
+        plain = DynamicCache()
+        with our_cls(compression_ratio=0.5, **kw)(model):
+            model.model(input_ids=ids, past_key_values=plain)
+        _assert_same_rows(ours, plain)
