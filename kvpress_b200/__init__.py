@@ -12,6 +12,7 @@ from kvpress_b200.presses.composed_press import ComposedPress
 from kvpress_b200.presses.compression_ratio_decoding_press import CompressionRatioDecodingPress
 from kvpress_b200.presses.decoding_press import DecodingPress
 from kvpress_b200.presses.expected_attention_press import ExpectedAttentionPress
+from kvpress_b200.presses.expected_attention_with_stats import ExpectedAttentionStatsPress
 from kvpress_b200.presses.key_rerotation_press import KeyRerotationPress
 from kvpress_b200.presses.keydiff_press import KeyDiffPress
 from kvpress_b200.presses.knorm_press import KnormPress
@@ -29,6 +30,7 @@ __all__ = [
     "KnormPress",
     "SnapKVPress",
     "ExpectedAttentionPress",
+    "ExpectedAttentionStatsPress",
     "StreamingLLMPress",
     "DecodingPress",
     "KeyRerotationPress",

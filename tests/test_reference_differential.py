@@ -293,3 +293,56 @@ def test_block_press_same_rows_as_reference(monkeypatch, ref, inner, block_size)
         with our_cls(compression_ratio=0.5, **kw)(model):
             model.model(input_ids=ids, past_key_values=plain)
         _assert_same_rows(ours, plain)
+
+
+def test_expected_attention_stats_press_same_rows_and_folder_layout_as_reference(monkeypatch, ref, tmp_path):
+    """expected_attention_with_stats.py:21-110: stored (mu, Sigma) per layer instead of the per-prompt prologue;
+    statistics folders are interchangeable with the reference's PyTorchModelHubMixin layout; the offline collector
+    reproduces the reference formula (mean, unbiased covariance of the pre-RoPE queries beyond n_sink)."""
+    from kvpress_b200 import ExpectedAttentionStatsPress
+    from kvpress_b200.presses.expected_attention_with_stats import ExpectedAttentionStats, collect_query_statistics
+    from kvpress.presses.expected_attention_with_stats import ExpectedAttentionStats as RefStats
+
+    cpu_backend.install(monkeypatch)
+    model = tiny_llama()
+    cfg = model.config
+    L, Hq, D = cfg.num_hidden_layers, cfg.num_attention_heads, cfg.head_dim
+    batches = [_distinct_ids(40 + i, n=120, batch=1) for i in range(3)]
+    stats = collect_query_statistics(model, batches, n_sink=4)
+    # independent restatement of the reference's collect_queries arithmetic
+    from kvpress_b200.utils import get_prerope_query_states
+    qs = [[] for _ in range(L)]
+    hooks = [layer.self_attn.register_forward_pre_hook(
+        lambda m, a, kw, i=i: qs[i].append(get_prerope_query_states(m, kw["hidden_states"])[:, :, 4:]), with_kwargs=True)
+        for i, layer in enumerate(model.model.layers)]
+    with torch.no_grad():
+        for ids in batches:
+            model.model(input_ids=ids)
+    for h in hooks:
+        h.remove()
+    for i in range(L):
+        q = torch.cat(qs[i], dim=-2)[0]                                     # [Hq, N, D]
+        mean = q.mean(dim=-2)
+        c = q - mean.unsqueeze(-2)
+        assert torch.allclose(stats.query_mean[i], mean, atol=1e-5)
+        assert torch.allclose(stats.query_cov[i], c.transpose(-2, -1) @ c / (q.shape[-2] - 1), atol=1e-5)
+
+    # folder layout: ours -> reference loader, reference -> our loader
+    stats.save_pretrained(str(tmp_path / "ours"))
+    theirs = RefStats.from_pretrained(str(tmp_path / "ours"))
+    assert torch.equal(theirs.query_mean.data, stats.query_mean.data) and torch.equal(theirs.query_cov.data, stats.query_cov.data)
+    theirs.save_pretrained(str(tmp_path / "theirs"))
+    back = ExpectedAttentionStats.from_pretrained(str(tmp_path / "theirs"))
+    assert torch.equal(back.query_cov.data, stats.query_cov.data) and back.meta["n_sink"] == 4
+
+    # the presses: same rows, with and without covariance; hidden states are not needed
+    ids = _distinct_ids(50)
+    for use_cov in (True, False):
+        rp = ref.ExpectedAttentionStatsPress(compression_ratio=0.5, use_covariance=use_cov, stats_folder=str(tmp_path / "ours"))
+        op = ExpectedAttentionStatsPress(compression_ratio=0.5, use_covariance=use_cov, stats_folder=str(tmp_path / "theirs"))
+        t_cache, o_cache = _prefill_both(rp, op, model, ids)
+        assert torch.equal(op.mu, rp.mu) and op.mu.shape == (L, Hq, D)
+        _assert_same_rows(o_cache, t_cache)
+    assert ExpectedAttentionStatsPress.needs_hidden_states is False
+    with pytest.raises(ValueError, match="No statistics given"):
+        ExpectedAttentionStatsPress(0.5).post_init_from_model(model)
