@@ -23,6 +23,7 @@ from kvpress_b200.presses.random_press import RandomPress
 from kvpress_b200.presses.scorer_press import ScorerPress
 from kvpress_b200.presses.snapkv_press import SnapKVPress
 from kvpress_b200.presses.streaming_llm_press import StreamingLLMPress
+from kvpress_b200.presses.tova_press import TOVAPress
 
 __all__ = [
     "BasePress",
@@ -32,6 +33,7 @@ __all__ = [
     "ExpectedAttentionPress",
     "ExpectedAttentionStatsPress",
     "StreamingLLMPress",
+    "TOVAPress",
     "DecodingPress",
     "KeyRerotationPress",
     "KeyDiffPress",

@@ -41,6 +41,7 @@ CASES = [
     ("snapkv", lambda m: m.SnapKVPress, SnapKVPress, {"window_size": 16, "kernel_size": 5}),
     ("expected_attention", lambda m: m.ExpectedAttentionPress, ExpectedAttentionPress, {"n_sink": 4}),
     ("keydiff", lambda m: m.KeyDiffPress, KeyDiffPress, {}),
+    ("tova", lambda m: m.TOVAPress, __import__("kvpress_b200").TOVAPress, {}),
 ]
 
 
