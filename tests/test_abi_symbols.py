@@ -115,3 +115,22 @@ def test_argument_validation_of_every_compress_entry_point_without_gpu():
         sizes.append(out.value)
     n = ctypes.c_int(0)
     assert lib.kvp_launches_per_compress(ctypes.byref(problem()), 99, ctypes.byref(n)) == -7
+
+
+def test_header_is_valid_c_and_links_from_c(tmp_path):
+    """include/kvpress_b200.h compiled as strict C99 by gcc, linked against the shared library, run without a GPU."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    native.load()
+    lib = native.library_path()
+    root = HEADER.parent.parent
+    exe = tmp_path / "check_abi"
+    subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", f"-I{root / 'include'}",
+                    str(root / "tests" / "c_abi" / "check_abi.c"), str(lib), f"-Wl,-rpath,{lib.parent}", "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("abi 1 knorm_ws ")
