@@ -12,5 +12,5 @@ for o in kvpress_b200/build/*.o; do
   b=$(basename $o)
   if [ "$b" = "${src%.cu}.o" ]; then objs="$objs tools/bin/obj_$name/$b"; else objs="$objs $o"; fi
 done
-nvcc -shared -cudart static -o tools/bin/libv_$name.so $objs
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o tools/bin/libv_$name.so $objs
 echo tools/bin/libv_$name.so
