@@ -51,7 +51,9 @@ struct EaScratch {
     float* logits;    // [R][G][S_pad]
     float* vnorm;     // [R][S_pad]
     float2* partial;  // [R][G][n_parts] (max, sum exp) per CTA part
-    uint16_t* cov_tri;  // [B*Hq][D][D] lower-triangular form of cov (KVP_EA_TRI builds only)
+#if KVP_EA_TRI
+    uint16_t* cov_tri;  // [B*Hq][D][D] lower-triangular form of cov
+#endif
 };
 
 static inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -79,7 +81,6 @@ static EaScratch carve_ea(const Dims& d, const Workspace& ws) {
     s.vnorm = reinterpret_cast<float*>(p);
     p += align256((size_t)d.R * S_pad * 4);
     s.partial = reinterpret_cast<float2*>(p);
-    s.cov_tri = nullptr;
 #if KVP_EA_TRI
     {
         const size_t n_parts = (size_t)((d.S + kScoreChunkGeneric - 1) / kScoreChunkGeneric);
