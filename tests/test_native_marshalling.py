@@ -130,3 +130,71 @@ def test_generic_scores_and_rerotation_operands(rec):
         native.scores_compress_rerotate(sc, k, v, 10, torch.rand(16))
     with pytest.raises(RuntimeError, match="scores must be"):
         native.scores_compress(sc[:, :2], k, v, 10)
+
+
+# ---- the presses added late in round 1, driven through the REAL native wrappers (recording library) ---------------
+class _Attn(torch.nn.Module):
+    """Minimal attention module: what the presses read (head_dim, layer_idx, config, q_proj, rotary_emb)."""
+
+    def __init__(self, hidden=64, heads=4, kv_heads=2, head_dim=16):
+        super().__init__()
+        from types import SimpleNamespace
+        self.head_dim, self.layer_idx = head_dim, 0
+        self.config = SimpleNamespace(num_attention_heads=heads, num_key_value_heads=kv_heads, num_hidden_layers=2,
+                                      _attn_implementation="sdpa")
+        self.q_proj = torch.nn.Linear(hidden, heads * head_dim, bias=False).to(torch.bfloat16)
+        inv_freq = 1.0 / (10000.0 ** (torch.arange(0, head_dim, 2).float() / head_dim))
+
+        def rotary(x, positions):
+            ang = positions[..., None].float() * inv_freq
+            emb = torch.cat((ang, ang), dim=-1)
+            return emb.cos().to(x.dtype), emb.sin().to(x.dtype)
+        self.rotary_emb = rotary
+        self.rotary_emb.inv_freq = inv_freq
+
+
+def _press_inputs(S=60):
+    torch.manual_seed(0)
+    attn = _Attn()
+    hidden = torch.randn(2, S, 64).to(torch.bfloat16)
+    keys, values = torch.randn(2, 2, S, 16).to(torch.bfloat16), torch.randn(2, 2, S, 16).to(torch.bfloat16)
+    cos, sin = attn.rotary_emb(hidden, torch.arange(S)[None])
+    return attn, hidden, keys, values, {"position_embeddings": (cos, sin)}
+
+
+def test_tova_press_marshalling(rec):
+    from kvpress_b200 import TOVAPress
+    attn, hidden, keys, values, kwargs = _press_inputs()
+    k2, v2 = TOVAPress(0.5).compress(attn, hidden, keys, values, None, kwargs)
+    names = [c[0] for c in rec.calls]
+    assert names == ["kvp_expected_attention_score", "kvp_scores_compress"]
+    _, p, a = rec.calls[0]
+    assert (p["B"], p["Hkv"], p["Hq"], p["S"], p["D"]) == (2, 2, 4, 60, 16)
+    assert a[3] == 0 and a[5] == 0 and a[6] == 0            # no covariance, n_sink = 0, no value norms
+    assert rec.calls[1][1]["n_kept"] == 30 and k2.shape == (2, 2, 30, 16)
+
+
+def test_chunkkv_press_marshalling(rec):
+    from kvpress_b200 import ChunkKVPress, KnormPress
+    attn, hidden, keys, values, kwargs = _press_inputs(S=70)
+    k2, _ = ChunkKVPress(KnormPress(0.5), chunk_length=20).compress(attn, hidden, keys, values, None, kwargs)
+    names = [c[0] for c in rec.calls]
+    assert names == ["kvp_knorm_score", "kvp_scores_compress"]
+    _, p, a = rec.calls[1]
+    assert a[1] == (0, 0)                                    # the 0/1 chunk mask is one broadcast row
+    assert p["n_kept"] in (40, 30) and k2.shape[2] == p["n_kept"]   # 2 of 4 chunks: 2 full ones, or 1 full + the 10-token tail
+
+
+def test_stats_press_marshalling(rec):
+    from kvpress_b200 import ExpectedAttentionStatsPress
+    attn, hidden, keys, values, kwargs = _press_inputs()
+    press = ExpectedAttentionStatsPress(0.5)
+    press.mu = torch.randn(2, 4, 16).to(torch.bfloat16)
+    a_ = torch.randn(2, 4, 16, 16)
+    press.cov = (a_ @ a_.transpose(-1, -2)).to(torch.bfloat16)
+    press.compress(attn, hidden, keys, values, None, kwargs)
+    name, p, a = rec.calls[-1]
+    assert name == "kvp_expected_attention_compress" and p["Hq"] == 4 and a[3] != 0 and a[5] == 4
+    press.use_covariance = False
+    press.compress(attn, hidden, keys, values, None, kwargs)
+    assert rec.calls[-1][2][3] == 0
