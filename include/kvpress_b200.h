@@ -29,9 +29,13 @@
  *   - Selection rule: the n_kept largest scores per (b, h) row; ties at the threshold are
  *     resolved towards the LOWEST position (deterministic; torch.topk leaves it unspecified).
  *   - Caller owns all memory (outputs + workspace of kvp_workspace_bytes()). The library
- *     allocates nothing, keeps no mutable global state, never synchronises the stream, and is
- *     re-entrant per (stream, workspace). (ExpectedAttention enqueues its ||v|| kernel on an internal
- *     per-device side stream joined back into the caller's stream before the call returns.)
+ *     allocates no device memory and never synchronises the stream (kvp_workspace_check and the *_host
+ *     convenience call excepted). Process-wide state is limited to write-once caches of device
+ *     properties (SM count, occupancy, function attributes) and, for ExpectedAttention with
+ *     use_vnorm, ONE internal side stream + two events per device: the ||v|| kernel is forked onto it
+ *     and joined back into the caller's stream before the call returns; host threads enqueueing
+ *     ExpectedAttention calls on the same device serialise on a mutex for those few microseconds.
+ *     Calls are re-entrant per (stream, workspace); every call is CUDA-graph capturable.
  *   - Return value: KVP_OK (0) or a negative kvp_status. No exceptions cross this boundary.
  */
 #ifndef KVPRESS_B200_H
@@ -56,7 +60,8 @@ typedef enum kvp_status {
     KVP_ERR_BAD_STRIDE = -4,
     KVP_ERR_WORKSPACE_TOO_SMALL = -5,
     KVP_ERR_CUDA = -6,
-    KVP_ERR_BAD_ARGUMENT = -7
+    KVP_ERR_BAD_ARGUMENT = -7,
+    KVP_ERR_KERNEL_TIMEOUT = -8 /* a kernel abandoned a bounded wait: outputs invalid (library bug) */
 } kvp_status;
 
 typedef enum kvp_dtype { KVP_BF16 = 0, KVP_F16 = 1 } kvp_dtype;
@@ -92,6 +97,13 @@ const char* kvp_last_cuda_error(void);
 
 /* Bytes of scratch a *_compress / *_score call of this scorer needs (256-byte aligned). */
 int kvp_workspace_bytes(const kvp_problem* p, int scorer, size_t* bytes_out);
+
+/* Debugging aid. The persistent select / compact kernels wait on each other with BOUNDED spins; a wait that
+ * expires raises a flag in the workspace instead of trapping the CUDA context. This call synchronises
+ * `stream`, reads the flag of the last call that used `workspace` and returns KVP_OK or
+ * KVP_ERR_KERNEL_TIMEOUT. Never needed for correct operation. */
+int kvp_workspace_check(const kvp_problem* p, int scorer, const void* workspace, size_t workspace_bytes,
+                        kvp_stream_t stream);
 
 /* Number of kernel launches (incl. memset nodes) one *_compress call enqueues; bench.py
  * reports it as gpu_launches. */

@@ -2,6 +2,7 @@
 CUDA behind the reference's own press API (BasePress / ScorerPress hooks and the
 "kv-press-text-generation" pipeline). See DESIGN.md for scope and INTEGRATION.md for the C ABI.
 """
+from kvpress_b200.attention_patch import patch_attention_functions
 from kvpress_b200.pipeline import KVPressTextGenerationPipeline
 from kvpress_b200.presses.adakv_press import AdaKVPress
 from kvpress_b200.presses.base_press import SUPPORTED_MODELS, BasePress
@@ -24,6 +25,10 @@ from kvpress_b200.presses.scorer_press import ScorerPress
 from kvpress_b200.presses.snapkv_press import SnapKVPress
 from kvpress_b200.presses.streaming_llm_press import StreamingLLMPress
 from kvpress_b200.presses.tova_press import TOVAPress
+
+# Like the reference (kvpress/__init__.py:8,52): every attention function of transformers is wrapped at import,
+# so head-wise masking (AdaKV) and the cu_seq_lens_k repair after any press shortened a cache are always live.
+patch_attention_functions()
 
 __all__ = [
     "BasePress",

@@ -129,6 +129,7 @@ const char* kvp_status_string(int status) {
         case KVP_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
         case KVP_ERR_CUDA: return "CUDA error (see kvp_last_cuda_error)";
         case KVP_ERR_BAD_ARGUMENT: return "bad argument";
+        case KVP_ERR_KERNEL_TIMEOUT: return "a kernel abandoned a bounded wait (outputs invalid)";
         default: return "unknown status";
     }
 }
@@ -143,6 +144,23 @@ int kvp_workspace_bytes(const kvp_problem* p, int scorer, size_t* bytes_out) {
     // window only changes the SnapKV scratch; size for the largest supported window
     *bytes_out = layout(d, scorer, 256).total;
     return KVP_OK;
+}
+
+int kvp_workspace_check(const kvp_problem* p, int scorer, const void* workspace, size_t workspace_bytes,
+                        kvp_stream_t stream) {
+    Dims d;
+    int rc = validate(p, &d, false);
+    if (rc) return rc;
+    Workspace ws;
+    WsLayout L;
+    if ((rc = carve(d, scorer, 256, const_cast<void*>(workspace), workspace_bytes, &ws, &L))) return rc;
+    uint32_t flag = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemcpyAsync(&flag, ws.counters + kCounterErrSlot(d.R), sizeof(flag),
+                                    cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail_cuda(e);
+    return flag ? KVP_ERR_KERNEL_TIMEOUT : KVP_OK;
 }
 
 int kvp_launches_per_compress(const kvp_problem* p, int scorer, int* launches_out) {

@@ -21,6 +21,11 @@ constexpr int kScoreChunkGeneric = 256;   // positions per CTA of the plain stre
 // order-preserving uint image of the largest valid score (for the reference's max+1 sentinel);
 // [2+2R, 2+3R) score items done per row (fused Knorm kernel)
 __host__ __device__ constexpr int kCounterMaxSlot(int R) { return 1 + 2 * R; }
+// [3R + 8]: error flag. A bounded spin-wait that expires (a lost work item: library bug, or a device that
+// cannot co-schedule the persistent grid) raises it instead of trapping the whole CUDA context; every CTA
+// polls it with its ticket and drains. The host reads it back with kvp_workspace_check().
+__host__ __device__ constexpr int kCounterErrSlot(int R) { return 3 * R + 8; }
+constexpr uint32_t kSpinLimit = 1u << 22;  // x 64 ns nanosleep ~ 0.3 s
 
 struct Strides3 {
     int64_t b, h, s;
@@ -220,6 +225,37 @@ __device__ __forceinline__ void flush_chunk_keys(const uint16_t* skeys, const ui
         __syncthreads();
         flush_row_hist(shist, row, ws);
     }
+}
+
+// ---- host: per-device launch properties, resolved once per (device, kernel) and cached (tmap.cu) ----
+// Nothing below is re-queried on the launch path: the C-ABI calls are host-latency sensitive
+// (DecodingPress compactions, per-layer prefill hooks).
+int device_sm_count();                         // SM count of the CURRENT device
+constexpr int kMaxDevices = 64;
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device)
+template <typename Kern>
+static inline cudaError_t ensure_dynamic_smem(Kern kern, int bytes) {
+    static unsigned long long done = 0;  // bit per device; a lost race only repeats the idempotent call
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < kMaxDevices && ((done >> dev) & 1ull)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < kMaxDevices) done |= 1ull << dev;
+    return e;
+}
+// resident CTAs per SM of a kernel (occupancy query) once per (kernel instantiation, device)
+template <typename Kern>
+static inline int cached_ctas_per_sm(Kern kern, int threads, int dyn_smem = 0) {
+    static int cache[kMaxDevices] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    if (cache[dev] == 0) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, dyn_smem);
+        cache[dev] = per_sm > 0 ? per_sm : 1;
+    }
+    return cache[dev];
 }
 
 // ---- launchers implemented in the .cu files (host, C++ linkage) -------------------------------

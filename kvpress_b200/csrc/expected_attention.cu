@@ -687,13 +687,7 @@ static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* 
                                       int n_sink, const Workspace& ws, const EaScratch& sc,
                                       int* n_parts_out, cudaStream_t st, int g_off = 0) {
     using L = EaSmem<D, G>;
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (sm_count <= 0) sm_count = 148;
-    }
+    const int sm_count = device_sm_count();
     const int n_tiles128 = (d.S + kEaTile - 1) / kEaTile;
     int ctas_per_row = sm_count / d.R;
     if (ctas_per_row < 1) ctas_per_row = 1;
@@ -735,7 +729,7 @@ static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* 
     }
     const int smem = L::kTotal + 1024;
     auto kern = ea_logits_kernel<T, D, G>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kEaThreads, smem, st>>>(mapK, mapCov, static_cast<const T*>(mu), d.H, d.Hq, d.S, n_sink, d.R,
                                          n_tiles128, ctas_per_row, ctas_per_row, sc, ws.S_pad, d.Hq / d.H, g_off);

@@ -177,6 +177,7 @@ struct SelectSmem {
     int item;
     int b1;
     int last;
+    int abort;
 };
 
 // Row scan, executed by the CTA that finished the LAST refine item of a row: exact threshold T,
@@ -365,11 +366,17 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
     if (tid == 0) {
         const volatile unsigned long long* slot =
             reinterpret_cast<const volatile unsigned long long*>(ws.tile_prefix + (size_t)row * ws.n_tiles + tile);
+        volatile uint32_t* err = ws.counters + kCounterErrSlot(ws.R);
         uint32_t spins = 0;
         unsigned long long raw = *slot;
+        sm.abort = 0;
         while ((uint32_t)raw == 0u || (uint32_t)(raw >> 32) == 0u) {
             __nanosleep(64);
-            if (++spins > (1u << 24)) __trap();
+            if (++spins > kSpinLimit) *err = 1u;          // raise: the host reports it, nobody traps
+            if ((spins & 255u) == 0u && *err != 0u) {     // raised here or by another CTA: drain
+                sm.abort = 1;
+                break;
+            }
             raw = *slot;
         }
         const uint2 v = make_uint2((uint32_t)raw, (uint32_t)(raw >> 32));
@@ -378,6 +385,7 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
         sm.thr[1] = v.y - 1u;
     }
     __syncthreads();
+    if (sm.abort) return;
     SEL_ACC(0, t_wait);
     SEL_T0(t_rank);
     const uint32_t key = __ldcg(&ws.keys[(size_t)row * ws.S_pad + s]);
@@ -477,18 +485,9 @@ select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, St
     SEL_ACC(7, t_kernel);
 }
 
-static int persistent_grid(const void* kernel, int threads, int n_items) {
-    static int sm_count = 0;
-    int dev = 0;
-    if (sm_count == 0) {
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (sm_count <= 0) sm_count = 148;
-    }
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
-    if (per_sm <= 0) per_sm = 1;
-    const int grid = sm_count * per_sm;
+template <typename Kern>
+static int persistent_grid(Kern kernel, int threads, int n_items) {
+    const int grid = device_sm_count() * cached_ctas_per_sm(kernel, threads);
     return n_items < grid ? n_items : grid;
 }
 
@@ -499,7 +498,7 @@ static cudaError_t launch_select_compact_t(const Dims& d, const void* K, const v
     const int n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
     const int n_items = d.R * n_groups + d.R * ws.n_tiles;
     auto kern = select_compact_kernel<TR>;
-    const int grid = persistent_grid(reinterpret_cast<const void*>(kern), kTileThreads, n_items);
+    const int grid = persistent_grid(kern, kTileThreads, n_items);
     kern<<<grid, kTileThreads, 0, st>>>(static_cast<const char*>(K), static_cast<const char*>(V), d.ks, d.vs,
                                         static_cast<char*>(K_out), static_cast<char*>(V_out), idx_out, d.H,
                                         d.S, d.D, d.n_kept, ws, inv_freq);
@@ -573,14 +572,17 @@ __device__ __forceinline__ FusedItem decode_fused_item(long long item, int R, in
     return it;
 }
 
-__device__ __forceinline__ void spin_until(const uint32_t* counter, uint32_t need) {
+// Returns false when the wait was abandoned (error flag raised): the caller skips its item.
+__device__ __forceinline__ bool spin_until(const uint32_t* counter, uint32_t need, volatile uint32_t* err) {
     const volatile uint32_t* flag = counter;
     uint32_t spins = 0;
     while (*flag < need) {
         __nanosleep(64);
-        if (++spins > (1u << 24)) __trap();  // a bug must not hang the GPU
+        if (++spins > kSpinLimit) *err = 1u;  // a bug must not hang the GPU (nor trap the context)
+        if ((spins & 255u) == 0u && *err != 0u) return false;
     }
     __threadfence();
+    return true;
 }
 
 template <typename T, int LPR>
@@ -612,8 +614,10 @@ knorm_fused_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks
             __syncthreads();
             if (tid == 0) atomicAdd(&score_done[it.row], 1u);
         } else if (it.kind == 1) {
-            if (tid == 0) spin_until(&score_done[it.row], (uint32_t)nT);
+            if (tid == 0)
+                sm.abort = spin_until(&score_done[it.row], (uint32_t)nT, ws.counters + kCounterErrSlot(R)) ? 0 : 1;
             __syncthreads();
+            if (sm.abort) continue;
             refine_item(sm, it.row, it.idx, nA, S, n_kept, ws);
         } else {
             compact_item(sm, it.row, it.idx, reinterpret_cast<const char*>(K),
@@ -634,7 +638,7 @@ static cudaError_t launch_knorm_fused_t(const Dims& d, const void* K, const void
 #define KVP_LAUNCH_FUSED(LPR)                                                                         \
     do {                                                                                              \
         auto kern = knorm_fused_kernel<T, LPR>;                                                       \
-        const int grid = persistent_grid(reinterpret_cast<const void*>(kern), kTileThreads, (int)total); \
+        const int grid = persistent_grid(kern, kTileThreads, (int)total); \
         kern<<<grid, kTileThreads, 0, st>>>(static_cast<const T*>(K), static_cast<const T*>(V), d.ks,  \
                                             d.vs, static_cast<char*>(K_out), static_cast<char*>(V_out), \
                                             idx_out, static_cast<uint16_t*>(scores_out), d.H, d.S, d.D, \

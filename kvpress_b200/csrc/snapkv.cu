@@ -559,13 +559,7 @@ template <typename T, int D, int NQP>
 static cudaError_t launch_snap_t(const Dims& d, int dtype, const void* K, const void* q_window, int window,
                                  int kernel_size, const Workspace& ws, void* scores_out, cudaStream_t st) {
     using L = SnSmem<D, NQP>;
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (sm_count <= 0) sm_count = 148;
-    }
+    const int sm_count = device_sm_count();
     const int G = d.Hq / d.H;
     const int NQ = G * window;
     const SnapScratch sc = carve_snap(d, window, ws);
@@ -601,9 +595,9 @@ static cudaError_t launch_snap_t(const Dims& d, int dtype, const void* K, const 
     const int smem = L::kTotal + 1024;
     auto k1 = snap_stats_kernel<T, D, NQP>;
     auto k2 = snap_colsum_kernel<T, D, NQP>;
-    cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = ensure_dynamic_smem(k1, smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = ensure_dynamic_smem(k2, smem);
     if (e != cudaSuccess) return e;
 
     k1<<<grid, kSnThreads, smem, st>>>(mapK, mapQ, d.H, G, d.S, window, d.R, n_tiles128, ctas_per_row,

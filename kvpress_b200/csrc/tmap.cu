@@ -1,8 +1,23 @@
-// tmap.cu — host-side TMA tensor-map encoding. The driver symbol cuTensorMapEncodeTiled is fetched
+// tmap.cu — host-side helpers: cached device properties and TMA tensor-map encoding. The driver symbol cuTensorMapEncodeTiled is fetched
 // through cudaGetDriverEntryPoint so the library has no link-time dependency on libcuda.
+#include "common.cuh"
 #include "umma.cuh"
 
 namespace kvp {
+
+// SM count of the current device, cached per device index (heterogeneous / MIG hosts size their
+// persistent grids per device).
+int device_sm_count() {
+    static int cache[kMaxDevices] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    if (cache[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev] = n > 0 ? n : 148;
+    }
+    return cache[dev];
+}
 
 kvp_encode_tiled_fn get_encode_tiled() {
     static kvp_encode_tiled_fn fn = nullptr;  // immutable once resolved

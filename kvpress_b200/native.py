@@ -53,6 +53,7 @@ SIGNATURES = {
     "kvp_last_cuda_error": (ctypes.c_char_p, []),
     "kvp_workspace_bytes": (ctypes.c_int, [_PP, ctypes.c_int, ctypes.POINTER(_SZ)]),
     "kvp_launches_per_compress": (ctypes.c_int, [_PP, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "kvp_workspace_check": (ctypes.c_int, [_PP, ctypes.c_int, _P, _SZ, _P]),
     "kvp_knorm_score": (ctypes.c_int, [_PP, _P, _P, _P]),
     "kvp_knorm_compress": (ctypes.c_int, [_PP, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "kvp_streaming_score": (ctypes.c_int, [_PP, _I, _P, _P]),
@@ -158,7 +159,23 @@ def _strides(t: torch.Tensor):
     return tuple(int(t.stride(d)) if t.shape[d] > 1 else 0 for d in range(3))
 
 
+_PROBLEMS: dict = {}
+
+
 def make_problem(keys: torch.Tensor, values: torch.Tensor, n_kept: int, num_q_heads: Optional[int] = None) -> KvpProblem:
+    """kvp_problem of one call. Structs are cached per (shape, strides, n_kept, Hq, dtype) and must be treated
+    as read-only by callers: DecodingPress / per-layer hooks repeat the same few problems thousands of times."""
+    key = (keys.shape, keys.stride(), values.stride(), int(n_kept), num_q_heads, keys.dtype)
+    p = _PROBLEMS.get(key)
+    if p is None:
+        p = _build_problem(keys, values, n_kept, num_q_heads)
+        if len(_PROBLEMS) > 1024:
+            _PROBLEMS.clear()
+        _PROBLEMS[key] = p
+    return p
+
+
+def _build_problem(keys: torch.Tensor, values: torch.Tensor, n_kept: int, num_q_heads: Optional[int] = None) -> KvpProblem:
     B, H, S, D = keys.shape
     p = KvpProblem()
     p.B, p.Hkv, p.S, p.D = B, H, S, D
@@ -172,18 +189,54 @@ def make_problem(keys: torch.Tensor, values: torch.Tensor, n_kept: int, num_q_he
     return p
 
 
-def _stream() -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
-def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
-    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device, as an integer handle."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    """Raw address (0 = NULL); ctypes converts ints to void* through the declared argtypes."""
+    return 0 if t is None else t.data_ptr()
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _guard(device: torch.device):
+    """Device guard only when the tensor's device is not the current one (the common per-layer hook call
+    skips the set-device round trip)."""
+    if device.type != "cuda" or device.index is None or device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
+_WS_BYTES: dict = {}
 
 
 def workspace_bytes(p: KvpProblem, scorer: int) -> int:
-    out = _SZ(0)
-    _check(load().kvp_workspace_bytes(ctypes.byref(p), scorer, ctypes.byref(out)), "kvp_workspace_bytes")
-    return int(out.value)
+    """kvp_workspace_bytes, asked once per (shape, scorer)."""
+    key = (p.B, p.Hkv, p.Hq, p.S, p.D, p.dtype, scorer)
+    n = _WS_BYTES.get(key)
+    if n is None:
+        out = _SZ(0)
+        _check(load().kvp_workspace_bytes(ctypes.byref(p), scorer, ctypes.byref(out)), "kvp_workspace_bytes")
+        n = _WS_BYTES[key] = int(out.value)
+        if len(_WS_BYTES) > 4096:
+            _WS_BYTES.clear()
+    return n
 
 
 def launches_per_compress(p: KvpProblem, scorer: int) -> int:
@@ -202,8 +255,71 @@ def _alloc_out(keys: torch.Tensor, n_kept: int, want_idx: bool, want_scores: boo
     return k_out, v_out, idx, scores
 
 
+_WS_CACHE: dict = {}
+
+
 def _workspace(p: KvpProblem, scorer: int, device) -> torch.Tensor:
-    return torch.empty(workspace_bytes(p, scorer), dtype=torch.uint8, device=device)
+    """Scratch for one call. Calls on one stream execute in order, so one grow-only buffer per (device, stream)
+    is reused instead of allocated per call; under CUDA-graph capture a fresh buffer from the graph's pool is
+    used (it must live exactly as long as the graph)."""
+    need = workspace_bytes(p, scorer)
+    if device.type != "cuda":
+        return torch.empty(need, dtype=torch.uint8, device=device)
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(need, dtype=torch.uint8, device=device)
+    key = (device.index, _stream())
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < need:
+        if len(_WS_CACHE) > 64:
+            _WS_CACHE.clear()
+        ws = _WS_CACHE[key] = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
+    return ws
+
+
+# --------------------------------------------------------------------------------------------------
+# captured calls: one compress call bound to fixed tensors, replayed as ONE graph launch
+# --------------------------------------------------------------------------------------------------
+class GraphedCall:
+    """`fn()` (any sequence of native.* calls on fixed input tensors) captured into a CUDA graph.
+
+    The C-ABI calls only enqueue kernels / memset nodes on the current stream (the ExpectedAttention side
+    stream forks from and joins back into it), never synchronise and never allocate, so they are capturable
+    as they are. `replay()` costs one cudaGraphLaunch on the host instead of 1-6 launches + their argument
+    marshalling: it makes the call GPU-bound on any host (DecodingPress compactions, repeated same-shape
+    prefill layers, bench.py). Outputs are the tensors `fn` returned; they are overwritten by every replay.
+    The inputs must stay alive and at the same addresses (update them in place)."""
+
+    def __init__(self, fn, warmup: int = 2):
+        if not torch.cuda.is_available():
+            raise RuntimeError("GraphedCall needs a CUDA device")
+        self._fn = fn
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up off the capture: lazy inits (func attributes, side stream, ...)
+            for _ in range(max(1, warmup)):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn()
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs
+
+    __call__ = replay
+
+
+def capture(fn, warmup: int = 2) -> GraphedCall:
+    return GraphedCall(fn, warmup)
+
+
+def workspace_check(p: KvpProblem, scorer: int, workspace: torch.Tensor) -> None:
+    """Raises if a kernel of the last call on this workspace abandoned a bounded wait (kvp_workspace_check;
+    synchronises the current stream). Debugging aid: the wait only expires on a library bug."""
+    _check(load().kvp_workspace_check(ctypes.byref(p), scorer, _ptr(workspace), workspace.numel(), _stream()),
+           "kvp_workspace_check")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -214,7 +330,7 @@ def knorm_score(keys: torch.Tensor) -> torch.Tensor:
     keys = _normalise(keys)
     p = make_problem(keys, keys, 0)
     scores = torch.empty(keys.shape[:3], dtype=keys.dtype, device=keys.device)
-    with torch.cuda.device(keys.device):
+    with _guard(keys.device):
         _check(load().kvp_knorm_score(ctypes.byref(p), _ptr(keys), _ptr(scores), _stream()), "kvp_knorm_score")
     return scores
 
@@ -226,7 +342,7 @@ def knorm_compress(keys, values, n_kept: int, return_indices: bool = False, retu
     p = make_problem(keys, values, n_kept)
     k_out, v_out, idx, scores = _alloc_out(keys, n_kept, return_indices, return_scores)
     if n_kept > 0:
-        with torch.cuda.device(keys.device):
+        with _guard(keys.device):
             ws = _workspace(p, SCORER_KNORM, keys.device)
             _check(
                 load().kvp_knorm_compress(
@@ -245,7 +361,7 @@ def keydiff_score(keys: torch.Tensor) -> torch.Tensor:
     keys = _normalise(keys)
     p = make_problem(keys, keys, 0)
     scores = torch.empty(keys.shape[:3], dtype=keys.dtype, device=keys.device)
-    with torch.cuda.device(keys.device):
+    with _guard(keys.device):
         ws = _workspace(p, SCORER_KEYDIFF, keys.device)
         _check(load().kvp_keydiff_score(ctypes.byref(p), _ptr(keys), _ptr(scores), _ptr(ws), ws.numel(), _stream()),
                "kvp_keydiff_score")
@@ -259,7 +375,7 @@ def keydiff_compress(keys, values, n_kept: int, return_indices: bool = False, re
     p = make_problem(keys, values, n_kept)
     k_out, v_out, idx, scores = _alloc_out(keys, n_kept, return_indices, return_scores)
     if n_kept > 0:
-        with torch.cuda.device(keys.device):
+        with _guard(keys.device):
             ws = _workspace(p, SCORER_KEYDIFF, keys.device)
             _check(
                 load().kvp_keydiff_compress(
@@ -277,7 +393,7 @@ def streaming_score(keys: torch.Tensor, n_kept: int, n_sink: int) -> torch.Tenso
     _require_cuda_kv(keys, keys)
     p = make_problem(keys, keys, n_kept)
     scores = torch.empty(keys.shape[:3], dtype=keys.dtype, device=keys.device)
-    with torch.cuda.device(keys.device):
+    with _guard(keys.device):
         _check(load().kvp_streaming_score(ctypes.byref(p), n_sink, _ptr(scores), _stream()), "kvp_streaming_score")
     return scores
 
@@ -289,7 +405,7 @@ def streaming_compress(keys, values, n_kept: int, n_sink: int, return_indices: b
     p = make_problem(keys, values, n_kept)
     k_out, v_out, idx, _ = _alloc_out(keys, n_kept, return_indices, False)
     if n_kept > 0:
-        with torch.cuda.device(k_out.device):
+        with _guard(k_out.device):
             _check(
                 load().kvp_streaming_compress(
                     ctypes.byref(p), n_sink, _ptr(keys), _ptr(values), _ptr(k_out), _ptr(v_out), _ptr(idx), _stream()),
@@ -316,7 +432,7 @@ def snapkv_score(keys, q_window, window: int, kernel_size: int) -> torch.Tensor:
     q_window = _check_q(q_window, keys, window)
     p = make_problem(keys, keys, 0, q_window.shape[1])
     scores = torch.empty(keys.shape[:3], dtype=keys.dtype, device=keys.device)
-    with torch.cuda.device(keys.device):
+    with _guard(keys.device):
         ws = _workspace(p, SCORER_SNAPKV, keys.device)
         _check(
             load().kvp_snapkv_score(
@@ -335,7 +451,7 @@ def snapkv_compress(keys, values, q_window, window: int, kernel_size: int, n_kep
     p = make_problem(keys, values, n_kept, q_window.shape[1])
     k_out, v_out, idx, scores = _alloc_out(keys, n_kept, return_indices, return_scores)
     if n_kept > 0:
-        with torch.cuda.device(keys.device):
+        with _guard(keys.device):
             ws = _workspace(p, SCORER_SNAPKV, keys.device)
             _check(
                 load().kvp_snapkv_compress(
@@ -367,7 +483,7 @@ def expected_attention_score(keys, values, mu, cov, epsilon: float, n_sink: int,
     mu, cov = _check_stats(mu, cov, keys)
     p = make_problem(keys, values, 0, mu.shape[1])
     scores = torch.empty(keys.shape[:3], dtype=keys.dtype, device=keys.device)
-    with torch.cuda.device(keys.device):
+    with _guard(keys.device):
         ws = _workspace(p, SCORER_EXPECTED_ATTENTION, keys.device)
         _check(
             load().kvp_expected_attention_score(
@@ -386,7 +502,7 @@ def expected_attention_compress(keys, values, mu, cov, epsilon: float, n_sink: i
     p = make_problem(keys, values, n_kept, mu.shape[1])
     k_out, v_out, idx, scores = _alloc_out(keys, n_kept, return_indices, return_scores)
     if n_kept > 0:
-        with torch.cuda.device(keys.device):
+        with _guard(keys.device):
             ws = _workspace(p, SCORER_EXPECTED_ATTENTION, keys.device)
             _check(
                 load().kvp_expected_attention_compress(
@@ -414,7 +530,7 @@ def scores_compress(scores: torch.Tensor, keys, values, n_kept: int, return_indi
     if n_kept > 0:
         sstride = (ctypes.c_int64 * 2)(
             scores.stride(0) if scores.shape[0] > 1 else 0, scores.stride(1) if scores.shape[1] > 1 else 0)
-        with torch.cuda.device(keys.device):
+        with _guard(keys.device):
             ws = _workspace(p, SCORER_GENERIC, keys.device)
             _check(
                 load().kvp_scores_compress(
@@ -438,7 +554,7 @@ def scores_select(scores: torch.Tensor, n_kept: int) -> torch.Tensor:
     idx = torch.empty((B, H, n_kept), dtype=torch.int32, device=scores.device)
     if n_kept > 0:
         sstride = (ctypes.c_int64 * 2)(scores.stride(0) if B > 1 else 0, scores.stride(1) if H > 1 else 0)
-        with torch.cuda.device(scores.device):
+        with _guard(scores.device):
             ws = _workspace(p, SCORER_GENERIC, scores.device)
             _check(load().kvp_scores_select(ctypes.byref(p), _ptr(scores), sstride, _ptr(idx), _ptr(ws), ws.numel(),
                                             _stream()), "kvp_scores_select")
@@ -463,7 +579,7 @@ def scores_compress_rerotate(scores: torch.Tensor, keys, values, n_kept: int, in
     if n_kept > 0:
         sstride = (ctypes.c_int64 * 2)(
             scores.stride(0) if scores.shape[0] > 1 else 0, scores.stride(1) if scores.shape[1] > 1 else 0)
-        with torch.cuda.device(keys.device):
+        with _guard(keys.device):
             ws = _workspace(p, SCORER_GENERIC, keys.device)
             _check(
                 load().kvp_scores_compress_rerotate(

@@ -9,7 +9,9 @@ Differences that do not change results:
   * decoding is detected from Python ints (no `.item()` sync per layer per token);
   * hidden states are only buffered (and cloned) when the wrapped press reads them
     (`needs_hidden_states`); Knorm / StreamingLLM never do, which removes a [B,1,hidden] clone per
-    layer per generated token;
+    layer per generated token. A press that reads only the LENGTH of the buffered hidden states
+    (`needs_hidden_states_len`: ExpectedAttentionStatsPress derives the future RoPE positions from it)
+    gets a zero-copy stride-0 view of the length the reference's buffer would have;
   * the compaction itself is the fused sm_100a path of the wrapped press.
 """
 from __future__ import annotations
@@ -67,6 +69,7 @@ class DecodingPress(BasePress):
         assert self.compression_interval > 0, "compression_interval must be greater than 0"
         assert self.target_size > 0, "target_size must be greater than 0"
         self.hidden_states_buffer = defaultdict(list)  # layer_idx -> list of [B, q, hidden]
+        self.hidden_states_lens = defaultdict(list)    # layer_idx -> q_len of every buffered chunk (length-only presses)
         self.layer_step_counts = defaultdict(int)
         if self.base_press.compression_ratio:
             logger.warning(
@@ -105,8 +108,12 @@ class DecodingPress(BasePress):
             return output  # prefill is some other press's business
 
         buffering = self.hidden_states_buffer_size > 0 and getattr(self.base_press, "needs_hidden_states", True)
+        length_only = (not buffering and self.hidden_states_buffer_size > 0
+                       and getattr(self.base_press, "needs_hidden_states_len", False))
         if buffering:
             self.hidden_states_buffer[layer_idx].append(hidden_states.detach().clone())
+        elif length_only:
+            self.hidden_states_lens[layer_idx].append(q_len)
         self.layer_step_counts[layer_idx] += 1
 
         target = self._resolve_target_size(kwargs)
@@ -117,6 +124,9 @@ class DecodingPress(BasePress):
             attentions = output[1] if len(output) > 1 and output[1] is not None else None
             if buffering:
                 buffered = torch.cat(self.hidden_states_buffer[layer_idx], dim=1)
+            elif length_only:  # same shape as the reference's concatenated buffer, no data
+                total = sum(self.hidden_states_lens[layer_idx])
+                buffered = hidden_states[:, :1].expand(-1, total, -1)
             else:
                 buffered = hidden_states
             keys, values = self.compress(module, buffered, keys, values, attentions, kwargs)
@@ -124,13 +134,17 @@ class DecodingPress(BasePress):
             write_back(cache, layer_idx, keys, values)
             self.layer_step_counts[layer_idx] = 0
             self.hidden_states_buffer[layer_idx] = []  # buffer and cache must stay aligned
+            self.hidden_states_lens[layer_idx] = []
 
         if buffering:
             self.hidden_states_buffer[layer_idx] = self.hidden_states_buffer[layer_idx][-self.hidden_states_buffer_size:]
+        elif length_only:
+            self.hidden_states_lens[layer_idx] = self.hidden_states_lens[layer_idx][-self.hidden_states_buffer_size:]
         return output
 
     def reset(self):
         self.hidden_states_buffer = defaultdict(list)
+        self.hidden_states_lens = defaultdict(list)
         self.layer_step_counts = defaultdict(int)
 
     @contextmanager

@@ -76,7 +76,8 @@ class ExpectedAttentionStatsPress(ExpectedAttentionPress):
     mu: torch.Tensor = field(init=False, default=None)    # [L, Hq, D], set in post_init_from_model (or by hand)
     cov: torch.Tensor = field(init=False, default=None)   # [L, Hq, D, D]
 
-    needs_hidden_states = False
+    needs_hidden_states = False      # the stored statistics replace the prompt's queries ...
+    needs_hidden_states_len = True   # ... but q_len (= hidden_states.shape[1]) places the future RoPE positions
 
     def get_query_statistics(self, module: nn.Module, hidden_states: torch.Tensor):
         """This layer's stored statistics, rotated to the positions after the current context, for every batch row."""

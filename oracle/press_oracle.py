@@ -188,6 +188,78 @@ def snapkv_scores_fp32(q_window, keys, window: int, kernel_size: int) -> torch.T
 
 
 # --------------------------------------------------------------------------------------------------
+# tova_press.py:35-61: attention of the LAST query over all keys, mean over ALL heads
+# --------------------------------------------------------------------------------------------------
+def window_attention(q_window: torch.Tensor, keys: torch.Tensor, window: int) -> torch.Tensor:
+    """snapkv_press.py:60-69 from the RoPE'd window queries on: [B,Hq,w,S-w] attention weights (16-bit)."""
+    B, Hkv, S, D = keys.shape
+    G = q_window.shape[1] // Hkv
+    attn = torch.matmul(q_window, repeat_kv(keys, G).transpose(2, 3)) / math.sqrt(D)
+    mask = torch.triu(torch.ones_like(attn) * float("-inf"), diagonal=S - window + 1)
+    attn = attn + mask
+    attn = F.softmax(attn, dim=-1, dtype=torch.float32).to(q_window.dtype)
+    return attn[..., :-window]
+
+
+def tova_scores(q_last: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
+    """q_last [B,Hq,D] = RoPE'd query of the last position -> [B,Hkv,S] (tova_press.py:47-59): window attention
+    with window 1, mean over dim 1 (all query heads), the one row repeated for every kv head, last position padded
+    with max + 1."""
+    attn = window_attention(q_last.unsqueeze(2), keys, 1)       # [B,Hq,1,S-1]
+    scores = attn.mean(1)                                       # [B,1,S-1]
+    scores = scores.repeat(1, keys.shape[1], 1)
+    return F.pad(scores, (0, 1), value=scores.max().item() + 1)
+
+
+def tova_scores_fp32(q_last: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
+    """Same formula in fp32 throughout; the forced last position is +inf."""
+    B, Hkv, S, D = keys.shape
+    G = q_last.shape[1] // Hkv
+    logits = torch.einsum("bhd,bhsd->bhs", q_last.float(), repeat_kv(keys, G).float()) / math.sqrt(D)
+    p = F.softmax(logits, dim=-1)[..., :-1].mean(1, keepdim=True)
+    return F.pad(p.repeat(1, Hkv, 1), (0, 1), value=float("inf"))
+
+
+# --------------------------------------------------------------------------------------------------
+# chunkkv_press.py:52-117 and block_press.py:49-98: wrappers over a score tensor / a score function
+# --------------------------------------------------------------------------------------------------
+def chunkkv_chunk_scores(scores: torch.Tensor, chunk_length: int) -> torch.Tensor:
+    """chunkkv_press.py:78-92 — per-chunk score [B, n_chunks]: heads summed, mean over the chunk; a ragged tail is
+    one more chunk."""
+    S = scores.shape[-1]
+    n_full, tail = divmod(S, chunk_length)
+    main = scores[..., : n_full * chunk_length].sum(dim=1).view(-1, n_full, chunk_length).mean(dim=-1)
+    if tail > 0:
+        main = torch.cat([main, scores[..., -tail:].sum(dim=1).mean(dim=-1, keepdim=True)], dim=-1)
+    return main
+
+
+def chunkkv_kept_positions(chunk_scores: torch.Tensor, S: int, chunk_length: int, compression_ratio: float):
+    """chunkkv_press.py:95-113 — positions of the kept chunks, ascending; batch element 0 decides for the batch."""
+    n_full, tail = divmod(S, chunk_length)
+    n_chunks = n_full + (tail > 0)
+    n_chunks_kept = max(1, int(n_chunks * (1 - compression_ratio)))
+    top = chunk_scores.topk(n_chunks_kept, dim=-1).indices[0]
+    pos = []
+    for c in top.tolist():
+        pos.append(torch.arange(c * chunk_length, min((c + 1) * chunk_length, S)))
+    return torch.cat(pos).sort().values
+
+
+def block_kept_positions(score_fn, B: int, H: int, S: int, n_kept: int, block_size: int) -> torch.Tensor:
+    """block_press.py:66-92 — iterative re-selection; score_fn(current_positions [B,H,n]) -> scores [B,H,n].
+    The per-round top-k uses the lowest-position tie rule of the kernels (torch.topk leaves ties open)."""
+    block = min(block_size, S)
+    kept = torch.arange(n_kept).expand(B, H, -1)
+    for lo in range(n_kept, S, block):
+        hi = min(lo + block, S)
+        current = torch.cat([kept, torch.arange(lo, hi).expand(B, H, -1)], dim=-1)
+        sel = select_lowest_index_ties(score_fn(current), n_kept)
+        kept = current.gather(-1, sel)
+    return kept
+
+
+# --------------------------------------------------------------------------------------------------
 # expected_attention_press.py:62-165
 # --------------------------------------------------------------------------------------------------
 def avg_rope_matrix(cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:

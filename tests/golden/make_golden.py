@@ -196,7 +196,65 @@ def make_keydiff():
     print("keydiff", out["cases"].tolist())
 
 
+def large_inputs(seed: int, B: int, Hkv: int, S: int, D: int, hidden: int, dtype=torch.bfloat16):
+    """Seeded inputs of the large case, regenerated (not stored) by the tests: explicit CPU generator, fixed draw
+    order. A checksum stored next to the outputs detects an RNG that no longer matches."""
+    g = torch.Generator().manual_seed(seed)
+    hidden_states = torch.randn(B, S, hidden, generator=g).to(dtype)
+    keys = torch.randn(B, Hkv, S, D, generator=g).to(dtype)
+    values = torch.randn(B, Hkv, S, D, generator=g).to(dtype)
+    return hidden_states, keys, values
+
+
+def tensor_checksum(*tensors) -> np.ndarray:
+    return np.array([int(t.contiguous().view(torch.int16).to(torch.int64).sum()) for t in tensors], dtype=np.int64)
+
+
+def make_large(name="large32k", *, B=1, Hq=4, Hkv=1, D=128, hidden=256, S=32768, seed=21):
+    """The four in-scope scorers + TOVA at a 32k context, reference run unmodified on CPU. Only the q_proj weight,
+    the outputs and an input checksum are stored; K, V and the hidden states are regenerated from the seed."""
+    kvpress = import_reference()
+    from transformers import LlamaConfig
+    from transformers.models.llama.modeling_llama import LlamaAttention, LlamaRotaryEmbedding
+
+    torch.manual_seed(seed)
+    cfg = LlamaConfig(hidden_size=hidden, num_attention_heads=Hq, num_key_value_heads=Hkv, head_dim=D,
+                      num_hidden_layers=1, intermediate_size=2 * hidden, vocab_size=128,
+                      max_position_embeddings=65536, rope_theta=500000.0)
+    cfg._attn_implementation = "sdpa"
+    attn = LlamaAttention(cfg, 0).to(torch.bfloat16).eval()
+    attn.rotary_emb = LlamaRotaryEmbedding(cfg)
+    hidden_states, keys, values = large_inputs(seed, B, Hkv, S, D, hidden)
+    cos, sin = attn.rotary_emb(hidden_states, torch.arange(S)[None])
+    kwargs = {"position_embeddings": (cos, sin)}
+    out = {"meta": np.array([B, Hq, Hkv, D, hidden, S, seed], dtype=np.int64),
+           "checksum": tensor_checksum(hidden_states, keys, values),
+           "q_weight": u16(attn.q_proj.weight.detach()), "rope_theta": np.array([500000.0])}
+    ratios = [0.5, 0.7]
+    out["ratios"] = np.array(ratios)
+    with torch.no_grad():
+        presses = {
+            "knorm": kvpress.KnormPress(),
+            "snap": kvpress.SnapKVPress(window_size=64, kernel_size=5),
+            "ea": kvpress.ExpectedAttentionPress(),
+            "tova": kvpress.TOVAPress(),
+        }
+        mu, cov = presses["ea"].get_query_statistics(attn, hidden_states)
+        out["ea_mu"], out["ea_cov"] = u16(mu), u16(cov)
+        for tag, press in presses.items():
+            sc = press.score(attn, hidden_states, keys, values, None, kwargs)
+            out[f"{tag}_scores"] = u16(sc)
+            for i, r in enumerate(ratios):
+                idx = sc.topk(int(S * (1 - r)), dim=-1).indices
+                out[f"{tag}_kept_{i}"] = idx.sort(-1).values.numpy().astype(np.int32)
+    np.savez_compressed(OUT / f"{name}.npz", **out)
+    print(name, {k: v.shape for k, v in out.items() if k.endswith("scores")})
+
+
 if __name__ == "__main__":
+    if "--large-only" in sys.argv:
+        make_large()
+        sys.exit(0)
     if "--keydiff-only" in sys.argv:
         make_keydiff()
         sys.exit(0)
@@ -210,3 +268,4 @@ if __name__ == "__main__":
     make_decoding_table()
     make_rerotation()
     make_keydiff()
+    make_large()

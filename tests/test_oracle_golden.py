@@ -154,3 +154,40 @@ def test_keydiff_oracle_matches_reference_and_its_fp32_form():
         assert d[~near_zero].max().item() <= 8 and (d[~near_zero] <= 2).float().mean().item() > 0.97, tag
         if near_zero.any():
             assert (hi.float() - ref_scores.float()).abs()[near_zero].max().item() < 2.0 ** -8
+
+
+def test_large32k_oracle_matches_reference():
+    """S = 32768 (tests/golden/large32k.npz; inputs regenerated from the seed): the oracle restatements of Knorm, the
+    SnapKV / TOVA window attention, the ExpectedAttention prologue and scan are bit-exact at a long context too."""
+    from transformers import LlamaConfig
+    from transformers.models.llama.modeling_llama import LlamaRotaryEmbedding
+
+    from tests.golden.make_golden import large_inputs, tensor_checksum
+
+    z = np.load(GOLDEN_DIR / "large32k.npz")
+    B, Hq, Hkv, D, hidden, S, seed = (int(x) for x in z["meta"])
+    h, k, v = large_inputs(seed, B, Hkv, S, D, hidden)
+    assert (tensor_checksum(h, k, v) == z["checksum"]).all(), "torch CPU RNG no longer reproduces the seeded inputs"
+
+    def t(name):
+        return torch.from_numpy(z[name].copy()).view(torch.bfloat16)
+
+    cfg = LlamaConfig(hidden_size=hidden, num_attention_heads=Hq, num_key_value_heads=Hkv, head_dim=D,
+                      max_position_embeddings=65536, rope_theta=500000.0)
+    rot = LlamaRotaryEmbedding(cfg)
+    cos, sin = rot(h, torch.arange(S)[None])
+    qw = t("q_weight")
+    assert torch.equal(O.knorm_scores(k), t("knorm_scores"))
+    q_last = O.snapkv_window_queries(h, qw, Hq, D, cos, sin, 1)[:, :, 0]
+    assert torch.equal(O.tova_scores(q_last, k), t("tova_scores"))
+    q_win = O.snapkv_window_queries(h, qw, Hq, D, cos, sin, 64)
+    assert torch.equal(O.snapkv_scores(q_win, k, 64, 5), t("snap_scores"))
+    cf, sf = rot(h, torch.arange(S, S + 512)[None])
+    mu, cov = O.expected_attention_stats(h, qw, Hq, D, cf[0], sf[0], 4)
+    assert torch.equal(mu, t("ea_mu")) and torch.equal(cov, t("ea_cov"))
+    assert torch.equal(O.expected_attention_scores(k, v, mu, cov, 0.0, 4, True), t("ea_scores"))
+    for i, r in enumerate(z["ratios"]):
+        n_kept = O.kept_count(S, float(r))
+        for tag in ("knorm", "snap", "ea", "tova"):
+            kept = torch.from_numpy(z[f"{tag}_kept_{i}"].copy())
+            assert O.check_selection(t(f"{tag}_scores"), kept, n_kept)["ok"]

@@ -347,3 +347,100 @@ def test_expected_attention_stats_press_same_rows_and_folder_layout_as_reference
     assert ExpectedAttentionStatsPress.needs_hidden_states is False
     with pytest.raises(ValueError, match="No statistics given"):
         ExpectedAttentionStatsPress(0.5).post_init_from_model(model)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# pipeline-level differentials: the reference pipeline driven on the same model, with a pre-hook that
+# restores the `cache_position` kwarg transformers >= 5.3 no longer hands to attention modules
+# ---------------------------------------------------------------------------------------------------------------------
+def _restore_cache_position(model):
+    handles = []
+
+    def pre(module, args, kwargs):
+        if kwargs.get("cache_position") is None:
+            past = kwargs["past_key_values"].get_seq_length(module.layer_idx)
+            kwargs["cache_position"] = torch.arange(past, past + kwargs["hidden_states"].shape[1])
+        return args, kwargs
+
+    for layer in model.model.layers:
+        handles.append(layer.self_attn.register_forward_pre_hook(pre, with_kwargs=True))
+    return handles
+
+
+def _both_pipelines(ref, model):
+    from kvpress_b200 import KVPressTextGenerationPipeline
+    from tests.tiny_models import word_tokenizer
+
+    tok = word_tokenizer()
+    return ref.KVPressTextGenerationPipeline(model=model, tokenizer=tok), KVPressTextGenerationPipeline(model=model, tokenizer=tok)
+
+
+@pytest.mark.parametrize("family", ["llama", "qwen3"])
+def test_pipeline_with_key_rerotation_matches_reference(monkeypatch, ref, family):
+    """pipeline.py:231-232 of the reference: after KeyRerotationPress the question / answer positions continue from
+    the COMPRESSED length. Same answers, and the positions the model sees are the reference's."""
+    from kvpress_b200 import KeyRerotationPress
+    from tests.tiny_models import words
+
+    cpu_backend.install(monkeypatch)
+    model = tiny_llama() if family == "llama" else tiny_qwen3()
+    ref_pipe, our_pipe = _both_pipelines(ref, model)
+    context, questions = words(150, seed=3), [words(4, seed=4), words(6, seed=5)]
+    seen = {"ref": [], "ours": []}
+
+    def spy(tag):
+        def pre(module, args, kwargs):
+            if kwargs.get("position_ids") is not None:
+                seen[tag].append(kwargs["position_ids"].flatten().tolist())
+        return model.model.register_forward_pre_hook(pre, with_kwargs=True)
+
+    handles = _restore_cache_position(model) + [spy("ref")]
+    try:
+        theirs = ref_pipe(context, questions=questions, max_new_tokens=6,
+                          press=ref.KeyRerotationPress(ref.StreamingLLMPress(compression_ratio=0.4, n_sink=4)))
+    finally:
+        for h in handles:
+            h.remove()
+    h = spy("ours")
+    try:
+        ours = our_pipe(context, questions=questions, max_new_tokens=6,
+                        press=KeyRerotationPress(StreamingLLMPress(compression_ratio=0.4, n_sink=4)))
+    finally:
+        h.remove()
+    assert ours["answers"] == theirs["answers"]
+    assert seen["ours"] == seen["ref"] and len(seen["ours"]) > 2
+    n_kept = int(151 * (1 - 0.4))
+    assert seen["ours"][0][0] == n_kept          # the first question token sits right after the compacted cache
+
+
+def test_decoding_press_with_stats_press_matches_reference(monkeypatch, ref, tmp_path):
+    """DecodingPress(ExpectedAttentionStatsPress): the stats press reads only the LENGTH of the buffered hidden states
+    (future RoPE positions); the zero-copy length-only buffer must reproduce the reference's concatenated buffer."""
+    from kvpress_b200 import DecodingPress, ExpectedAttentionStatsPress
+    from kvpress_b200.presses.expected_attention_with_stats import collect_query_statistics
+    from tests.tiny_models import words
+
+    cpu_backend.install(monkeypatch)
+    model = tiny_llama()
+    stats = collect_query_statistics(model, [_distinct_ids(60 + i, n=100, batch=1) for i in range(2)], n_sink=4)
+    stats.save_pretrained(str(tmp_path / "stats"))
+    ref_pipe, our_pipe = _both_pipelines(ref, model)
+    context, question = words(60, seed=8), words(5, seed=9)
+    kw = dict(compression_interval=7, target_size=40, hidden_states_buffer_size=256)
+    # few future positions: the average RoPE rotation then depends visibly on where they start (q_len)
+    skw = dict(stats_folder=str(tmp_path / "stats"), n_future_positions=3)
+
+    rp = ref.DecodingPress(base_press=ref.ExpectedAttentionStatsPress(**skw), **kw)
+    theirs_cache, ours_cache = DynamicCache(), DynamicCache()
+    handles = _restore_cache_position(model)
+    try:
+        theirs = ref_pipe(context, question=question, max_new_tokens=24, press=rp, cache=theirs_cache)
+    finally:
+        for h in handles:
+            h.remove()
+    op = DecodingPress(base_press=ExpectedAttentionStatsPress(**skw), **kw)
+    ours = our_pipe(context, question=question, max_new_tokens=24, press=op, cache=ours_cache)
+    assert ours["answer"] == theirs["answer"]
+    assert [la.keys.shape[2] for la in ours_cache.layers] == [la.keys.shape[2] for la in theirs_cache.layers]
+    _assert_same_rows(ours_cache, theirs_cache)
+    assert not op.hidden_states_buffer and not op.hidden_states_lens     # reset on exit, nothing was cloned
