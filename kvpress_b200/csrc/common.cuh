@@ -201,10 +201,13 @@ __device__ __forceinline__ void flush_chunk_keys(const uint16_t* skeys, const ui
     // the keys buffer is padded to a multiple of kTile per row: unconditional vector store
     uint16_t* kdst = ws.keys + (size_t)row * ws.S_pad + s0;
     if (KPT == 4) {
-        uint2 pk;
-        pk.x = (uint32_t)k[0] | ((uint32_t)k[1 % KPT] << 16);
-        pk.y = (uint32_t)k[2 % KPT] | ((uint32_t)k[3 % KPT] << 16);
-        *reinterpret_cast<uint2*>(kdst) = pk;
+        // a KPT*256-position chunk may reach past the row's padding (S_pad is a multiple of 256 only)
+        if (s0 < ws.S_pad) {
+            uint2 pk;
+            pk.x = (uint32_t)k[0] | ((uint32_t)k[1 % KPT] << 16);
+            pk.y = (uint32_t)k[2 % KPT] | ((uint32_t)k[3 % KPT] << 16);
+            *reinterpret_cast<uint2*>(kdst) = pk;
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < KPT; ++i) kdst[i] = k[i];

@@ -24,12 +24,15 @@
 #include "knorm_chunk.cuh"
 #include "umma.cuh"
 
-// Prepared experiment, default off: the B operand of the quadratic form is the lower triangle
-// T[n][c] = cov[n][c] + cov[c][n] (c < n), cov[n][n] (c == n), 0 (c > n) built by ea_cov_tri_kernel into the
-// scratch, so for head_dim 128 the K-steps of the second 64-wide panel only feed the columns n >= 64:
-// 12 instead of 16 64-column K-step units per head (-25 % tensor cycles). k^T cov k is unchanged in exact arithmetic.
+// Triangular quadratic form (default on). k^T cov k = sum_n k_n (sum_{c<=n} T[n][c] k_c) with
+// T[n][c] = cov[n][c] + cov[c][n] (c < n), cov[n][n] (c == n), 0 (c > n), built once per call by ea_cov_tri_kernel
+// into the scratch (exact whenever cov is symmetric, <= 2^-9 relative per entry otherwise: one rounding of the sum).
+// The B operand of K-step k (contraction columns c in [16k, 16k+16)) then has no non-zero rows n < 16k, so the MMA
+// warp issues that step on rows [32*(k/2), D) only: per head 2*(128+96+64+32) = 640 instead of 1024 N-units at
+// head_dim 128 (-37.5 % tensor cycles), 2*(64+32) = 192 instead of 256 at head_dim 64. KVP_EA_TRI=0 restores the
+// dense schedule (used by the A/B harness).
 #ifndef KVP_EA_TRI
-#define KVP_EA_TRI 0
+#define KVP_EA_TRI 1
 #endif
 
 namespace kvp {
@@ -188,8 +191,11 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         const int hq0 = b * Hq + h * g_total + g_off;  // first of them in [B*Hq]
         __syncthreads();  // previous row fully drained (s_bias, s_cov, s_red reusable)
         for (int n = tid; n < G * D; n += kEaThreads) {
-            const float bias = bias_scale * F16Traits<T>::to_float(
-                                                reinterpret_cast<const uint16_t*>(mu)[(size_t)hq0 * D + n]);
+            // resident slot n / D may be a padding head (g_total not a multiple of the template's G): no bias
+            const float bias = (g_off + n / D < g_total)
+                                   ? bias_scale * F16Traits<T>::to_float(
+                                                      reinterpret_cast<const uint16_t*>(mu)[(size_t)hq0 * D + n])
+                                   : 0.f;
             const uint16_t hi = F16Traits<T>::from_float(bias);
             const uint16_t lo = F16Traits<T>::from_float(bias - F16Traits<T>::to_float(hi));
             *reinterpret_cast<uint4*>(s_bx + umma::k16_noswizzle_offset(n, 0)) =
@@ -243,16 +249,20 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                             const uint64_t da =
                                 umma::smem_desc_sw128(a_base + kp * (kEaTile * 128) + kk * 32);
 #if KVP_EA_TRI
-                            if (D == 128 && kp == 1) {
-                                // T is lower-triangular: k >= 64 only reaches the columns n >= 64 of every head
-                                // (rows 64..127 of the head's panel = +64 * 128 B; accumulator columns + 64)
-                                const uint32_t idesc64 = umma::instr_desc_f16(kEaTile, 64, F16Traits<T>::kMmaFormat);
+                            // rows n < row0 of T are zero in this K-step's columns: issue on rows [row0, D) of
+                            // every head (B rows are 128 B apart, 32 rows = four 1024-B swizzle atoms; the
+                            // accumulator columns shift by the same row0). k = 0 covers all columns, so every
+                            // later step accumulates.
+                            constexpr int kGran = 32;
+                            const int row0 = (k * 16 / kGran) * kGran;
+                            if (row0 > 0) {
+                                const uint32_t idesc_n = umma::instr_desc_f16(kEaTile, D - row0, F16Traits<T>::kMmaFormat);
 #pragma unroll
                                 for (int q = 0; q < HPH; ++q) {
-                                    const uint64_t db64 = umma::smem_desc_sw128(
+                                    const uint64_t dbq = umma::smem_desc_sw128(
                                         umma::smem_u32(s_cov + (kp * G + half * HPH + q) * L::kCovHeadPanel) +
-                                        64 * 128 + kk * 32);
-                                    umma::mma_f16_ss(tmem + buf * kBufCols + q * D + 64, da, db64, idesc64, 1);
+                                        row0 * 128 + kk * 32);
+                                    umma::mma_f16_ss(tmem + buf * kBufCols + q * D + row0, da, dbq, idesc_n, 1);
                                 }
                                 continue;
                             }
@@ -377,7 +387,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     for (int q = 0; q < HPH; ++q) {
                         const int g = half * HPH + q;
                         const float lg = acc[q] * inv_2d;
-                        if (valid && g < G) {
+                        if (valid && g < G && g_off + g < g_total) {
                             sc.logits[((size_t)row * g_total + g_off + g) * S_pad + s] = lg;
                             const float m_new = fmaxf(run_m[q], lg);
                             run_z[q] = run_z[q] * __expf(run_m[q] - m_new) + __expf(lg - m_new);
@@ -408,7 +418,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         }
         // ---- CTA-level softmax statistics of this (row, part) -> partial[row][g][part] ---------------
         __syncthreads();
-        if (tid < G) {
+        if (tid < G && g_off + tid < g_total) {
             // head g was accumulated in slot q of the warps of: both warpgroups (one half per tile,
             // tiles alternate) or warpgroup g / HPH (two halves per tile)
             const int g = tid, q = g % HPH;
@@ -549,25 +559,34 @@ ea_vnorm_kernel(const T* __restrict__ V, Strides3 vs, int H, int S, int D, float
 }
 
 // ---- finalize: softmax normalisation, group mean, * ||v||, ONE rounding, keys + histogram -----------
+// One CTA = kEaFinalPos consecutive positions of one row, 4 per thread: the G logits and the value norm arrive as
+// 128-bit loads (all independent, issued before anything else), 1024 CTAs cover a 128k x 8-head cache in one wave.
+constexpr int kEaFinalKpt = 4;
+constexpr int kEaFinalPos = kTileThreads * kEaFinalKpt;
 template <typename T>
 __global__ void __launch_bounds__(kTileThreads)
 ea_finalize_kernel(int G, int S, int n_sink, int use_vnorm, float eps, int n_parts, EaScratch sc,
                    Workspace ws, uint16_t* __restrict__ scores_out) {
-    __shared__ uint16_t skeys[kTile];
-    __shared__ uint16_t sscores[kTile];
+    constexpr int KPT = kEaFinalKpt;
+    __shared__ uint16_t skeys[kEaFinalPos];
+    __shared__ uint16_t sscores[kEaFinalPos];
     __shared__ uint32_t shist[256];
     __shared__ float s_m[8], s_iz[8];
     __shared__ float s_max[8];
-    static_assert(kFinalizeTiles == 1, "one 256-position tile per CTA");
-    const int tile = blockIdx.x, row = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk = blockIdx.x, row = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     shist[tid] = 0;
-    const int s = tile * kTile + tid;
-    const bool scored = (s < S) && (s >= n_sink);
-    // 1. independent loads first: this position's logits and (warps < G) the per-CTA softmax partials
-    float lg[8];
+    const int s0 = chunk * kEaFinalPos + tid * KPT;
+    const bool in_pad = s0 < ws.S_pad;  // the padded scratch rows are readable up to S_pad (a multiple of 256)
+    // 1. independent loads first: this thread's logits / norms and (warps < G) the per-CTA softmax partials
+    float4 lg[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g)
-        lg[g] = (g < G && scored) ? __ldcg(&sc.logits[((size_t)row * G + g) * ws.S_pad + s]) : 0.f;
+        lg[g] = (g < G && in_pad)
+                    ? __ldcg(reinterpret_cast<const float4*>(&sc.logits[((size_t)row * G + g) * ws.S_pad + s0]))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 vn4 = (use_vnorm && in_pad)
+                           ? __ldcg(reinterpret_cast<const float4*>(&sc.vnorm[(size_t)row * ws.S_pad + s0]))
+                           : make_float4(1.f, 1.f, 1.f, 1.f);
     float pm = -INFINITY, pz = 0.f;
     if (warp < G) {
         for (int p = lane; p < n_parts; p += 32) {
@@ -576,10 +595,7 @@ ea_finalize_kernel(int G, int S, int n_sink, int use_vnorm, float eps, int n_par
             pz = (mn == -INFINITY) ? 0.f : pz * __expf(pm - mn) + q.y * __expf(q.x - mn);
             pm = mn;
         }
-    }
-    const float vn = (use_vnorm && scored) ? __ldcg(&sc.vnorm[(size_t)row * ws.S_pad + s]) : 1.f;
-    // 3. exact softmax normalisers of the G heads
-    if (warp < G) {
+        // 2. exact softmax normalisers of the G heads
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
             const float m2 = __shfl_xor_sync(0xFFFFFFFFu, pm, off);
@@ -595,26 +611,35 @@ ea_finalize_kernel(int G, int S, int n_sink, int use_vnorm, float eps, int n_par
     }
     __syncthreads();
     float fmax_valid = -INFINITY;
-    uint16_t bits = 0, key = 0;
-    if (s < S) {
-        if (!scored) {
-            key = kForcedKey;
-        } else {
-            float p = 0.f;
+    const float vn[4] = {vn4.x, vn4.y, vn4.z, vn4.w};
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-                if (g < G) p += __expf(lg[g] - s_m[g]) * s_iz[g];
-            p *= (1.0f / (float)G);
-            const float score = use_vnorm ? (p + eps) * vn : p;
-            bits = F16Traits<T>::from_float(score);
-            key = ordered_key16(bits, F16Traits<T>::kInfBits);
-            fmax_valid = F16Traits<T>::to_float(bits);
+    for (int i = 0; i < KPT; ++i) {
+        const int s = s0 + i;
+        uint16_t bits = 0, key = 0;
+        if (s < S) {
+            if (s < n_sink) {
+                key = kForcedKey;
+            } else {
+                float p = 0.f;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    if (g < G) {
+                        const float l = (i == 0) ? lg[g].x : (i == 1) ? lg[g].y : (i == 2) ? lg[g].z : lg[g].w;
+                        p += __expf(l - s_m[g]) * s_iz[g];
+                    }
+                }
+                p *= (1.0f / (float)G);
+                const float score = use_vnorm ? (p + eps) * vn[i] : p;
+                bits = F16Traits<T>::from_float(score);
+                key = ordered_key16(bits, F16Traits<T>::kInfBits);
+                fmax_valid = fmaxf(fmax_valid, F16Traits<T>::to_float(bits));
+            }
         }
+        skeys[tid * KPT + i] = key;
+        sscores[tid * KPT + i] = bits;
     }
-    skeys[tid] = key;
-    sscores[tid] = bits;
     __syncthreads();
-    flush_chunk_keys<1, false>(skeys, sscores, shist, row, tile * kTile, S, ws, scores_out);
+    flush_chunk_keys<KPT, false>(skeys, sscores, shist, row, chunk * kEaFinalPos, S, ws, scores_out);
     // max over valid scores of the whole tensor (for the reference's max+1 sentinel)
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1)
@@ -715,14 +740,12 @@ static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* 
         const uint32_t box[3] = {64, (uint32_t)D, 1};
         const void* cov_src = cov;
 #if KVP_EA_TRI
-        if (D == 128) {
-            if (g_off == 0) {
-                ea_cov_tri_kernel<T><<<d.B * d.Hq, 256, 0, st>>>(static_cast<const uint16_t*>(cov), sc.cov_tri, D);
-                cudaError_t pe = cudaPeekAtLastError();
-                if (pe != cudaSuccess) return pe;
-            }
-            cov_src = sc.cov_tri;
+        if (g_off == 0) {  // (a second launch for the other four heads of a G = 8 group reuses it)
+            ea_cov_tri_kernel<T><<<d.B * d.Hq, 256, 0, st>>>(static_cast<const uint16_t*>(cov), sc.cov_tri, D);
+            cudaError_t pe = cudaPeekAtLastError();
+            if (pe != cudaSuccess) return pe;
         }
+        cov_src = sc.cov_tri;
 #endif
         cudaError_t e = make_tmap_16bit(&mapCov, cov_src, 3, dims, str, box);
         if (e != cudaSuccess) return e;
@@ -797,19 +820,21 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
         if ((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return e;
     }
     if (cov != nullptr) {
-        // tensor-core path: head_dim 64 or 128, up to 4 query heads per kv head resident in smem
-        if (d.D == 128 && G == 1) e = launch_ea_logits_t<T, 128, 1>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
-        else if (d.D == 128 && G == 2) e = launch_ea_logits_t<T, 128, 2>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
-        else if (d.D == 128 && G == 4) e = launch_ea_logits_t<T, 128, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
-        else if (d.D == 64 && G == 1) e = launch_ea_logits_t<T, 64, 1>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
-        else if (d.D == 64 && G == 2) e = launch_ea_logits_t<T, 64, 2>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
-        else if (d.D == 64 && G == 4) e = launch_ea_logits_t<T, 64, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
-        else if (G == 8 && (d.D == 128 || d.D == 64)) {
-            // eight query heads per kv head (Llama-3.1-70B): two launches of four resident Sigma each
-            for (int g_off = 0; g_off < 8 && e == cudaSuccess; g_off += 4)
-                e = (d.D == 128) ? launch_ea_logits_t<T, 128, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st, g_off)
-                                 : launch_ea_logits_t<T, 64, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st, g_off);
-        } else return cudaErrorNotSupported;
+        // tensor-core path: head_dim 64 or 128; 1, 2 or 4 query heads of a kv head resident in shared memory per
+        // launch. Other group sizes (3: Llama-3.2-3B, 5..8: Qwen2-7B has 7, Llama-3.1-70B 8) run on the 4-head
+        // instantiation with padding heads (no bias, nothing stored) and, above 4, a second launch for heads 4...
+        if (d.D != 128 && d.D != 64) return cudaErrorNotSupported;
+        const bool d128 = d.D == 128;
+        if (G == 1)
+            e = d128 ? launch_ea_logits_t<T, 128, 1>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st)
+                     : launch_ea_logits_t<T, 64, 1>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
+        else if (G == 2)
+            e = d128 ? launch_ea_logits_t<T, 128, 2>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st)
+                     : launch_ea_logits_t<T, 64, 2>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
+        else
+            for (int g_off = 0; g_off < G && e == cudaSuccess; g_off += 4)
+                e = d128 ? launch_ea_logits_t<T, 128, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st, g_off)
+                         : launch_ea_logits_t<T, 64, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st, g_off);
     } else {
         n_parts = (d.S + kScoreChunkGeneric - 1) / kScoreChunkGeneric;
         dim3 grid(n_parts, d.R);
@@ -834,7 +859,7 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
             if ((e = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return e;
         }
     }
-    dim3 grid2((ws.n_tiles + kFinalizeTiles - 1) / kFinalizeTiles, d.R);
+    dim3 grid2((d.S + kEaFinalPos - 1) / kEaFinalPos, d.R);
     ea_finalize_kernel<T><<<grid2, kTileThreads, 0, st>>>(G, d.S, n_sink, use_vnorm, eps, n_parts, sc, ws,
                                                           static_cast<uint16_t*>(scores_out));
     e = cudaPeekAtLastError();

@@ -143,9 +143,11 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
 
         if (warp == 0) {
             if (lane == 0) {
-                umma::mbar_arrive_expect_tx(q_full, (uint32_t)(L::kPanels * NQ * 128));
+                // all NQP resident rows are loaded (boxes of min(NQP, 256) rows): rows >= NQ belong to the next kv
+                // head or lie past the tensor (zero fill); their outputs are never read
+                umma::mbar_arrive_expect_tx(q_full, (uint32_t)(L::kPanels * NQP * 128));
                 for (int kp = 0; kp < L::kPanels; ++kp)
-                    for (int r0 = 0; r0 < NQ; r0 += 256)
+                    for (int r0 = 0; r0 < NQP; r0 += 256)
                         umma::tma_load_3d(s_q + kp * L::kQPanel + r0 * 128, &mapQ, q_full, kp * 64,
                                           q_row0 + r0, 0);
                 for (int t = t_begin; t < t_end; ++t, ++k_it) {
@@ -358,7 +360,9 @@ snap_colsum_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_consta
         for (int n = tid; n < NQP; n += kSnThreads) {
             // exact normaliser of query row n from the per-CTA partials of pass 1:
             // p[n, j] = exp2(c*y - m) / Z = exp2(c * (y + bias)),  bias = (-m - log2 Z) / c
-            float bias = 0.f;
+            // padding rows (n >= NQ): a bias that drives exp2(c * (y + bias)) to exactly 0, so a 16-column chunk
+            // that straddles NQ (windows that are not multiples of 16) adds nothing for them
+            float bias = -60000.f;
             if (n < NQ) {
                 float m = -INFINITY, z = 0.f;
                 const float2* part_n = sc.partial + ((size_t)row * NQ + n) * n_parts;
@@ -387,9 +391,11 @@ snap_colsum_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_consta
 
         if (warp == 0) {
             if (lane == 0) {
-                umma::mbar_arrive_expect_tx(q_full, (uint32_t)(L::kPanels * NQ * 128));
+                // all NQP resident rows are loaded (boxes of min(NQP, 256) rows): rows >= NQ belong to the next kv
+                // head or lie past the tensor (zero fill); their outputs are never read
+                umma::mbar_arrive_expect_tx(q_full, (uint32_t)(L::kPanels * NQP * 128));
                 for (int kp = 0; kp < L::kPanels; ++kp)
-                    for (int r0 = 0; r0 < NQ; r0 += 256)
+                    for (int r0 = 0; r0 < NQP; r0 += 256)
                         umma::tma_load_3d(s_q + kp * L::kQPanel + r0 * 128, &mapQ, q_full, kp * 64,
                                           q_row0 + r0, 0);
                 for (int t = t_begin; t < t_end; ++t, ++k_it) {
@@ -588,7 +594,7 @@ static cudaError_t launch_snap_t(const Dims& d, int dtype, const void* K, const 
         const uint64_t rows = (uint64_t)d.B * d.Hq * window;
         const uint64_t dims[3] = {(uint64_t)D, rows, 1};
         const uint64_t str[3] = {0, (uint64_t)D * 2, rows * D * 2};
-        const uint32_t box[3] = {64, (uint32_t)(NQ < 256 ? NQ : 256), 1};
+        const uint32_t box[3] = {64, (uint32_t)(NQP < 256 ? NQP : 256), 1};
         cudaError_t e = make_tmap_16bit(&mapQ, q_window, 3, dims, str, box);
         if (e != cudaSuccess) return e;
     }
@@ -622,9 +628,10 @@ static cudaError_t launch_snap_d(const Dims& d, int dtype, const void* K, const 
                                  int kernel_size, const Workspace& ws, void* scores_out, cudaStream_t st) {
     const int G = d.Hq / d.H;
     const int NQ = G * window;
-    if (NQ % 16 != 0 || NQ > 512 || (NQ > 256 && NQ != 512)) return cudaErrorNotSupported;
+    // any group size / window with G * window <= 512 query rows per kv head: the resident Q block is padded to
+    // 128 / 256 / 512 rows, padding rows are computed and ignored (Llama-3.2-3B: G = 3, Qwen2-7B: G = 7, ...)
+    if (NQ < 1 || NQ > 512) return cudaErrorNotSupported;
     const int NQP = NQ <= 128 ? 128 : (NQ <= 256 ? 256 : 512);
-    if (NQ > 128 && NQ != NQP) return cudaErrorNotSupported;  // TMEM blocks assume full 128-row halves
 #define KVP_SNAP(DD, NN) \
     if (d.D == DD && NQP == NN) return launch_snap_t<T, DD, NN>(d, dtype, K, q_window, window, kernel_size, ws, scores_out, st)
     KVP_SNAP(128, 128);

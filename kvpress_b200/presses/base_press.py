@@ -35,6 +35,12 @@ def _supported_models() -> tuple:
     return tuple(getattr(transformers, n) for n in names if hasattr(transformers, n))
 
 
+# Model classes the hooks are written for (same list as the reference, base_press.py:24-34). Shape limits of the
+# sm_100a library on top of that list: every scorer takes any head_dim that is a multiple of 8 (<= 256) EXCEPT the two
+# tensor-core scorers — SnapKVPress / PyramidKVPress and ExpectedAttentionPress with use_covariance=True — which need
+# head_dim 64 or 128, Hq/Hkv <= 8 and (Hq/Hkv) * window_size <= 512. Llama, Mistral, Qwen2 and Qwen3 checkpoints meet
+# them; Phi3 (head_dim 96) and Gemma3 (head_dim 256) raise "unsupported shape" for those two scorers — there is no
+# eager fallback by design (north_star: no CPU / multi-backend path).
 SUPPORTED_MODELS = _supported_models()
 
 

@@ -311,3 +311,65 @@ def test_expected_attention_stats_press_on_gpu(golden, use_cov):
     idx = O.select_lowest_index_ties(scores, n_kept)
     assert torch.equal(k2.cpu(), O.gather_rows(golden.t("keys"), idx))
     assert torch.equal(v2.cpu(), O.gather_rows(golden.t("values"), idx))
+
+
+# ---------------------------------------------------------------------------------------------------
+# group sizes / windows beyond the Llama-3.1 / Qwen3 layouts: padded tensor-core instantiations
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("G,D", [(3, 128), (5, 128), (7, 128), (6, 64), (3, 64)])
+def test_expected_attention_any_group_size(G, D):
+    """Llama-3.2-3B has G = 3, Qwen2-7B G = 7: the 4-head instantiation runs with padding heads (and a second launch
+    above 4). Scores vs the fp32 oracle, compress == canonical selection of its own scores."""
+    nat = _native()
+    torch.manual_seed(40 + G)
+    B, Hkv, S = 2, 2, 2500
+    Hq = Hkv * G
+    k = torch.randn(B, Hkv, S, D).to(torch.bfloat16)
+    v = torch.randn(B, Hkv, S, D).to(torch.bfloat16)
+    mu = (0.5 * torch.randn(B, Hq, D)).to(torch.bfloat16)
+    a = torch.randn(B, Hq, D, D) / D ** 0.5
+    cov = (a @ a.transpose(-1, -2)).to(torch.bfloat16)
+    n_kept = O.kept_count(S, 0.6)
+    k2, v2, idx, sc = nat.expected_attention_compress(k.to(DEV), v.to(DEV), mu.to(DEV), cov.to(DEV), 0.0, 4, True, n_kept,
+                                                      return_indices=True, return_scores=True)
+    hi = O.expected_attention_scores_fp32(k, v, mu, cov, 0.0, 4, True)
+    assert ulp16_diff(sc.cpu()[..., 4:], hi[..., 4:].to(torch.bfloat16)).max() <= 1
+    want = O.select_lowest_index_ties(sc.cpu(), n_kept)
+    assert torch.equal(idx.cpu().long(), want)
+    assert torch.equal(k2.cpu(), O.gather_rows(k, want)) and torch.equal(v2.cpu(), O.gather_rows(v, want))
+
+
+@pytest.mark.parametrize("G,w,D", [(3, 64, 128), (7, 64, 128), (4, 50, 128), (1, 16, 64), (5, 24, 64), (2, 7, 128)])
+def test_snapkv_any_group_size_and_window(G, w, D):
+    """G * window <= 512 query rows of any size: the resident Q block is padded to 128 / 256 / 512 rows."""
+    nat = _native()
+    torch.manual_seed(50 + G + w)
+    B, Hkv, S = 2, 2, 3000
+    Hq = Hkv * G
+    k = torch.randn(B, Hkv, S, D).to(torch.bfloat16)
+    v = torch.randn(B, Hkv, S, D).to(torch.bfloat16)
+    q_win = (1.5 * torch.randn(B, Hq, w, D)).to(torch.bfloat16)
+    n_kept = O.kept_count(S, 0.5)
+    k2, v2, idx, sc = nat.snapkv_compress(k.to(DEV), v.to(DEV), q_win.to(DEV), w, 5, n_kept, return_indices=True,
+                                          return_scores=True)
+    hi = O.snapkv_scores_fp32(q_win, k, w, 5)
+    assert ulp16_diff(sc.cpu()[..., : S - w], hi[..., : S - w].to(torch.bfloat16)).max() <= 1
+    want = O.select_lowest_index_ties(sc.cpu(), n_kept)
+    assert torch.equal(idx.cpu().long(), want) and (want[..., -w:] == torch.arange(S - w, S)).all()
+    assert torch.equal(k2.cpu(), O.gather_rows(k, want)) and torch.equal(v2.cpu(), O.gather_rows(v, want))
+
+
+def test_tensor_core_scorers_state_their_shape_limits():
+    """head_dim other than 64 / 128 (Phi3: 96, Gemma3: 256) has no tensor-core instantiation: a loud error, no
+    fallback."""
+    nat = _native()
+    k = torch.randn(1, 2, 600, 96, dtype=torch.bfloat16, device=DEV)
+    mu = torch.randn(1, 4, 96, dtype=torch.bfloat16, device=DEV)
+    cov = torch.eye(96, dtype=torch.bfloat16, device=DEV).expand(1, 4, 96, 96).contiguous()
+    with pytest.raises(RuntimeError, match="unsupported shape"):
+        nat.expected_attention_score(k, k, mu, cov, 0.0, 4, True)
+    with pytest.raises(RuntimeError, match="unsupported shape"):
+        nat.snapkv_score(k, torch.randn(1, 4, 64, 96, dtype=torch.bfloat16, device=DEV), 64, 5)
+    # the covariance-free scan and every streaming scorer take any head_dim that is a multiple of 8
+    assert nat.expected_attention_score(k, k, mu, None, 0.0, 4, False).shape == (1, 2, 600)
+    assert nat.knorm_score(k).shape == (1, 2, 600)

@@ -32,7 +32,10 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
     value = bench.whole_job_tokens_per_s(w["B"] * w["S"], world, job_ms)
     gathered = [None] * world
     dist.all_gather_object(gathered, float(K.float().sum()))
-    torch.save({"job_ms": job_ms, "value": value, "sums": gathered}, os.path.join(out_dir, f"r{rank}.pt"))
+    # configs[4]: layers pipeline-split over the ranks; every rank learns every rank's range
+    owned = [None] * world
+    dist.all_gather_object(owned, list(bench.layer_range(80, world, rank)))
+    torch.save({"job_ms": job_ms, "value": value, "sums": gathered, "owned": owned}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,3 +49,35 @@ def test_two_rank_bookkeeping(tmp_path):
         assert abs(res["value"] - 2 * 512 / 15e-3) < 1e-6   # aggregate of both shards
         assert res["sums"][0] != res["sums"][1]            # ranks synthesise different shards
     assert results[0]["sums"] == results[1]["sums"]
+    owned = results[0]["owned"]
+    assert owned == results[1]["owned"] and owned[0] == list(range(0, 40)) and owned[1] == list(range(40, 80))
+
+
+def test_layer_ranges_partition_the_model():
+    import bench
+
+    for n_layers in (80, 36, 32, 7):
+        for world in (1, 2, 4, 8):
+            got = [i for r in range(world) for i in bench.layer_range(n_layers, world, r)]
+            assert got == list(range(n_layers))                       # contiguous, disjoint, complete, in rank order
+    assert len(bench.layer_range(80, 8, 3)) == 10 and list(bench.layer_range(7, 8, 7)) == []
+
+
+def test_reference_arm_prints_what_it_ran():
+    """`bench.py --impl reference`: exactly --steps timed calls after --warmup, ms_per_step = the mean call time (the
+    driver checks steps x ms_per_step against its own clock), config identical to the B200 arm's, kind = reference
+    when oracle/_ref was built."""
+    import json
+    import subprocess
+    import time
+
+    t0 = time.time()
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1",
+                          "--workload", "knorm_128k", "--cpu-step-budget", "0.02"], capture_output=True, text=True, check=True)
+    wall = time.time() - t0
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["steps"] == 3 and line["warmup"] == 1 and line["gpu_launches"] == 0
+    assert line["steps"] * line["ms_per_step"] * 1e-3 < wall
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert set(line["config"]) >= {"workload", "S", "n_kept", "l2", "sharding"}
