@@ -15,7 +15,8 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libkvpress_b200.so"
 STAMP = PKG_DIR / "build" / "stamp.txt"
-SOURCES = ["api.cu", "knorm.cu", "keydiff.cu", "select_compact.cu", "snapkv.cu", "expected_attention.cu", "tmap.cu"]
+SOURCES = ["api.cu", "knorm.cu", "knorm_cluster.cu", "keydiff.cu", "select_compact.cu", "snapkv.cu", "expected_attention.cu",
+           "tmap.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

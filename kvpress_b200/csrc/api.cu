@@ -2,6 +2,7 @@
 // Validates the problem, carves the caller's workspace and enqueues the kernels on the caller's
 // stream. Never allocates, never synchronises (except the *_host convenience call), never throws.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -168,9 +169,12 @@ int kvp_launches_per_compress(const kvp_problem* p, int scorer, int* launches_ou
     switch (scorer) {
         case KVP_SCORER_STREAMING: *launches_out = 1; break;
         case KVP_SCORER_GENERIC: *launches_out = 3; break;  // memset, keys, select+compact
-        case KVP_SCORER_KNORM:  // memset + (fused | score, select+compact)
-            *launches_out = ((size_t)p->B * p->Hkv * p->S * p->D * 2 <= ((size_t)32 << 20)) ? 2 : 3;
+        case KVP_SCORER_KNORM: {  // cluster kernel | memset + (fused | score, select+compact)
+            Dims d;
+            if (validate(p, &d, false) == KVP_OK && knorm_cluster_applicable(d)) *launches_out = 1;
+            else *launches_out = ((size_t)p->B * p->Hkv * p->S * p->D * 2 <= ((size_t)32 << 20)) ? 2 : 3;
             break;
+        }
         case KVP_SCORER_KEYDIFF: *launches_out = 5; break;  // memset, anchor partials, merge, score, select+compact
         case KVP_SCORER_SNAPKV: *launches_out = 6; break;  // memset, stats, memset, colsum, finalize, select+compact
         case KVP_SCORER_EXPECTED_ATTENTION: *launches_out = 5; break;  // memset, logits, vnorm (side stream), finalize, select+compact
@@ -211,13 +215,20 @@ int kvp_knorm_compress(const kvp_problem* p, const void* K, const void* V, void*
     WsLayout L;
     if ((rc = carve(d, KVP_SCORER_KNORM, 0, workspace, workspace_bytes, &ws, &L))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(ws.hist_hi, 0, L.hist_bytes, st);
+    // DecodingPress-sized caches: one launch of the cluster kernel (knorm_cluster.cu), no memset, no scratch
+    cudaError_t e = launch_knorm_cluster(d, p->dtype, K, V, K_out, V_out, idx_out, scores_out, st);
+    if (e != cudaErrorNotSupported) return e == cudaSuccess ? KVP_OK : fail_cuda(e);
+    e = cudaMemsetAsync(ws.hist_hi, 0, L.hist_bytes, st);
     if (e != cudaSuccess) return fail_cuda(e);
-    // Small caches (DecodingPress compactions) are launch-latency-bound: one persistent kernel does
+    // Small caches beyond the cluster path are launch-latency-bound: one persistent kernel does
     // score + select + compact. Large caches measured faster as two kernels (the fused kernel's mixed
     // read/write item stream costs more HBM efficiency than the saved launch; K re-reads miss L2 anyway).
     const size_t k_bytes = (size_t)d.R * d.S * d.D * 2;
-    if (k_bytes <= ((size_t)32 << 20)) {
+    static const size_t fused_max_bytes = [] {  // A/B knob: KVP_KNORM_FUSED_MAX_MB (default 32)
+        const char* v = getenv("KVP_KNORM_FUSED_MAX_MB");
+        return (size_t)((v && *v) ? atoll(v) : 32) << 20;
+    }();
+    if (k_bytes <= fused_max_bytes) {
         e = launch_knorm_fused(d, p->dtype, K, V, K_out, V_out, idx_out, scores_out, ws, st);
         if (e != cudaErrorNotSupported) return e == cudaSuccess ? KVP_OK : fail_cuda(e);
     }

@@ -267,6 +267,9 @@ cudaError_t launch_knorm_score(const Dims& d, int dtype, const void* K, const Wo
 cudaError_t launch_knorm_fused(const Dims& d, int dtype, const void* K, const void* V, void* K_out,
                                void* V_out, int32_t* idx_out, void* scores_out, const Workspace& ws,
                                cudaStream_t st);
+bool knorm_cluster_applicable(const Dims& d);
+cudaError_t launch_knorm_cluster(const Dims& d, int dtype, const void* K, const void* V, void* K_out, void* V_out,
+                                 int32_t* idx_out, void* scores_out, cudaStream_t st);
 cudaError_t launch_keys_from_scores(const Dims& d, int dtype, const void* scores, int64_t sb, int64_t sh,
                                     const Workspace& ws, cudaStream_t st);
 cudaError_t launch_select_compact(const Dims& d, const void* K, const void* V, void* K_out,

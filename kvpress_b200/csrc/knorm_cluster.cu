@@ -1,0 +1,326 @@
+// knorm_cluster.cu — KnormPress score + top-k + compaction of a SMALL cache in ONE launch, no scratch, no memset:
+// the DecodingPress compaction (reference kvpress/presses/decoding_press.py:68-111 -> scorer_press.py:76-102 with
+// knorm_press.py:38 as the score), e.g. [1, 8, 2560, 128] -> [1, 8, 2048, 128] every 512 generated tokens per layer.
+//
+// At these sizes (tens of MB) the call is latency-bound: the multi-kernel path spends its time in launch gaps, a
+// memset node, global atomics and spin-waits between CTAs. Here one thread-block CLUSTER owns one (b, h) row:
+//   1. every CTA scores its slice of the row (128-bit loads, fp32 sum of squares, one rounding) and keeps the K rows
+//      it just read in shared memory;
+//   2. the 16-bit ordered keys of the slice are pushed into the shared memory of every CTA of the cluster
+//      (distributed shared memory), ONE cluster barrier;
+//   3. every CTA now holds the keys of the whole row and derives the exact threshold, the tie budget and the number
+//      of kept positions in front of its slice on its own (two 256-bin histograms + one counting pass);
+//   4. it ranks its slice and writes the kept K rows from shared memory and the kept V rows from global memory
+//      to their final places (ascending positions, ties to the lowest positions — same rule as select_compact.cu).
+// No global atomics, no flags, no workspace: the only inter-CTA communication is the key exchange.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace kvp {
+
+constexpr int kClThreads = 256;
+constexpr int kClMaxSmem = 200 * 1024;  // K slice + keys of the row + lists must fit one CTA's shared memory
+
+struct ClusterPlan {
+    int C;        // CTAs per cluster (= per row)
+    int P;        // positions per CTA (multiple of 8)
+    int smem;     // dynamic shared memory bytes
+    bool ok;
+};
+
+static ClusterPlan cluster_plan(const Dims& d, int C) {
+    ClusterPlan pl;
+    pl.C = C;
+    pl.P = ((d.S + C - 1) / C + 7) / 8 * 8;
+    const size_t ktile = (size_t)pl.P * d.D * 2;
+    const size_t keys = (size_t)C * pl.P * 2;
+    const size_t list = (size_t)pl.P * 4;
+    pl.smem = (int)(ktile + keys + list + 64);
+    pl.ok = pl.smem <= kClMaxSmem;
+    return pl;
+}
+
+template <typename T, int LPR>
+__global__ void __launch_bounds__(kClThreads, 1)
+knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks, Strides3 vs,
+                     char* __restrict__ K_out, char* __restrict__ V_out, int32_t* __restrict__ idx_out,
+                     uint16_t* __restrict__ scores_out, int H, int S, int D, int n_kept, int P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int row = blockIdx.y, b = row / H, h = row % H;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nvec = D >> 3;
+
+    int4* ktile = reinterpret_cast<int4*>(smem);                                        // [P][nvec] 16-byte pieces
+    uint16_t* all_keys = reinterpret_cast<uint16_t*>(smem + (size_t)P * D * 2);          // [C][P]
+    int* list = reinterpret_cast<int*>(smem + (size_t)P * D * 2 + (size_t)C * P * 2);    // [P] kept local positions
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t red[2][8];
+    __shared__ uint32_t thr[4];
+
+    // all CTAs of the cluster have started (their shared memory exists) before anyone writes into it
+    cluster.sync();
+
+    // ---- 1. score this CTA's slice [start, start + P) and stage its K rows -------------------------------------
+    const int start = rank * P;
+    uint16_t* my_keys = all_keys + (size_t)rank * P;
+    {
+        constexpr int RPW = 32 / LPR;
+        constexpr int ROWS_PER_PASS = (kClThreads / 32) * RPW;
+        constexpr int U = 4;
+        const int sub = lane % LPR, rsel = lane / LPR;
+        const T* base = K + (int64_t)b * ks.b + (int64_t)h * ks.h + (int64_t)sub * 8;
+        const int n_pass = (P + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
+#pragma unroll 1
+        for (int j0 = 0; j0 < n_pass; j0 += U) {
+            int4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = (j0 + u) * ROWS_PER_PASS + warp * RPW + rsel;
+                v[u] = make_int4(0, 0, 0, 0);
+                if (r < P && start + r < S && sub < nvec) v[u] = ldg_plain(base + (int64_t)(start + r) * ks.s);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = (j0 + u) * ROWS_PER_PASS + warp * RPW + rsel;
+                const bool in_slice = r < P;
+                const bool valid = in_slice && start + r < S;
+                if (valid && sub < nvec) ktile[(size_t)r * nvec + sub] = v[u];
+                const uint32_t w[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z, (uint32_t)v[u].w};
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = F16Traits<T>::unpack2(w[j]);
+                    ss = fmaf(f.x, f.x, ss);
+                    ss = fmaf(f.y, f.y, ss);
+                }
+#pragma unroll
+                for (int off = LPR / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
+                if (sub == 0 && in_slice) {
+                    uint16_t key = 0;
+                    if (valid) {
+                        // -sqrt(ss) rounded once to the storage dtype (negation is exact): knorm_press.py:38
+                        const uint16_t bits = F16Traits<T>::from_float(sqrtf(ss)) ^ 0x8000u;
+                        key = ordered_key16(bits, F16Traits<T>::kInfBits);
+                        if (scores_out != nullptr) scores_out[(size_t)row * S + start + r] = bits;
+                    }
+                    my_keys[r] = key;
+                }
+            }
+        }
+    }
+    hist[tid] = 0;
+    __syncthreads();
+
+    // ---- 2. all-gather of the keys through distributed shared memory ---------------------------------------------
+    {
+        const int n8 = P / 4;  // 8-byte pieces (4 keys) of the slice
+        const uint2* src = reinterpret_cast<const uint2*>(my_keys);
+        for (int peer = 1; peer < C; ++peer) {
+            const int dst_rank = (rank + peer) % C;  // spread the traffic over the peers
+            uint2* dst = reinterpret_cast<uint2*>(cluster.map_shared_rank(all_keys, dst_rank) + (size_t)rank * P);
+            for (int i = tid; i < n8; i += kClThreads) dst[i] = src[i];
+        }
+    }
+    cluster.sync();  // release / acquire at cluster scope: every slice of all_keys is complete everywhere
+
+    // ---- 3. exact threshold of the row, computed redundantly by every CTA -----------------------------------------
+    // position s of the row lives at all_keys[(s / P) * P + s % P] == all_keys[s] (slices are contiguous)
+    for (int s0 = 0; s0 < S; s0 += kClThreads) {  // uniform trip count: the warp votes below are full-mask
+        const int s = s0 + tid;
+        const unsigned bin = s < S ? (unsigned)(all_keys[s] >> 8) : 256u;
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
+        if (bin < 256u && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int b1;
+        uint32_t above1;
+        warp_suffix_find(hist, (uint32_t)n_kept, lane, b1, above1);
+        if (lane == 0) {
+            thr[0] = (uint32_t)b1;
+            thr[1] = (uint32_t)n_kept - above1;  // still needed from bin b1 (>= 1)
+        }
+    }
+    __syncthreads();
+    const unsigned b1 = thr[0];
+    const uint32_t need1 = thr[1];
+    hist[tid] = 0;
+    __syncthreads();
+    for (int s = tid; s < S; s += kClThreads) {
+        const unsigned k = all_keys[s];
+        if ((k >> 8) == b1) atomicAdd(&hist[k & 0xFF], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int lo1;
+        uint32_t above2;
+        warp_suffix_find(hist, need1, lane, lo1, above2);
+        if (lane == 0) {
+            thr[2] = (b1 << 8) | (uint32_t)lo1;  // threshold key T
+            thr[3] = need1 - above2;             // ties (key == T) to take, lowest positions first
+        }
+    }
+    __syncthreads();
+    const uint32_t T16 = thr[2], n_take = thr[3];
+
+    // kept (> T) and tied (== T) positions in front of this CTA's slice
+    uint32_t gt_b = 0, eq_b = 0;
+    const int front = min(start, S);
+    for (int s = tid; s < front; s += kClThreads) {
+        const uint32_t k = all_keys[s];
+        gt_b += k > T16;
+        eq_b += k == T16;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        gt_b += __shfl_xor_sync(0xFFFFFFFFu, gt_b, off);
+        eq_b += __shfl_xor_sync(0xFFFFFFFFu, eq_b, off);
+    }
+    if (lane == 0) {
+        red[0][warp] = gt_b;
+        red[1][warp] = eq_b;
+    }
+    __syncthreads();
+    uint32_t gt_before = 0, eq_before = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        gt_before += red[0][w];
+        eq_before += red[1][w];
+    }
+    __syncthreads();
+
+    // ---- 4. rank the slice (position order) and copy the kept rows ------------------------------------------------
+    uint32_t taken_eq = min(eq_before, n_take);  // ties already granted to lower positions
+    const uint32_t out_base = gt_before + taken_eq;
+    uint32_t count = 0;                          // kept rows of this slice so far
+    for (int c0 = 0; c0 < P; c0 += kClThreads) {
+        const int r = c0 + tid;
+        const bool valid = r < P && start + r < S;
+        const uint32_t key = valid ? my_keys[r] : 0u;
+        const bool is_gt = valid && key > T16;
+        const bool is_eq = valid && key == T16;
+        const unsigned m_gt = __ballot_sync(0xFFFFFFFFu, is_gt);
+        const unsigned m_eq = __ballot_sync(0xFFFFFFFFu, is_eq);
+        if (lane == 0) {
+            red[0][warp] = __popc(m_gt);
+            red[1][warp] = __popc(m_eq);
+        }
+        __syncthreads();
+        uint32_t gt_rank = __popc(m_gt & ((1u << lane) - 1u));
+        uint32_t eq_rank = __popc(m_eq & ((1u << lane) - 1u));
+        uint32_t tot_gt = 0, tot_eq = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            gt_rank += (w < warp) ? red[0][w] : 0u;
+            eq_rank += (w < warp) ? red[1][w] : 0u;
+            tot_gt += red[0][w];
+            tot_eq += red[1][w];
+        }
+        const uint32_t tie_room = n_take - taken_eq;  // ties this chunk may still take
+        if (is_gt || (is_eq && eq_rank < tie_room)) list[count + gt_rank + min(eq_rank, tie_room)] = r;
+        const uint32_t took = min(tot_eq, tie_room);
+        count += tot_gt + took;
+        taken_eq += took;
+        __syncthreads();
+    }
+    if (count == 0) return;
+    const int64_t out_row0 = (int64_t)row * n_kept + out_base;
+    if (idx_out != nullptr)
+        for (uint32_t i = tid; i < count; i += kClThreads) idx_out[out_row0 + i] = start + list[i];
+    const int64_t row_bytes = (int64_t)D * 2;
+    const char* v_src = reinterpret_cast<const char*>(V) + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2;
+    char* k_dst = K_out + out_row0 * row_bytes;
+    char* v_dst = V_out + out_row0 * row_bytes;
+    const uint64_t pol_first = l2_policy_evict_first();
+    const int total = (int)count * nvec;
+    constexpr int UC = 4;
+    for (int base = tid; base < total; base += kClThreads * UC) {
+        int4 vv[UC];
+#pragma unroll
+        for (int u = 0; u < UC; ++u) {
+            const int i = base + u * kClThreads;
+            if (i < total) {
+                const int r = i / nvec, cc = i - r * nvec;
+                vv[u] = ldg_hint(v_src + (int64_t)(start + list[r]) * vs.s * 2 + cc * 16, pol_first);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UC; ++u) {
+            const int i = base + u * kClThreads;
+            if (i < total) {
+                const int r = i / nvec, cc = i - r * nvec;
+                const int64_t off = (int64_t)r * row_bytes + cc * 16;
+                stg_hint(k_dst + off, ktile[(size_t)list[r] * nvec + cc], pol_first);
+                stg_hint(v_dst + off, vv[u], pol_first);
+            }
+        }
+    }
+}
+
+template <typename T, int LPR>
+static cudaError_t launch_cluster_t(const Dims& d, const ClusterPlan& pl, const void* K, const void* V, void* K_out,
+                                    void* V_out, int32_t* idx_out, void* scores_out, cudaStream_t st) {
+    auto kern = knorm_cluster_kernel<T, LPR>;
+    cudaError_t e = ensure_dynamic_smem(kern, kClMaxSmem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.C, d.R, 1);
+    cfg.blockDim = dim3(kClThreads, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pl.C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<const T*>(K), static_cast<const T*>(V), d.ks, d.vs,
+                              static_cast<char*>(K_out), static_cast<char*>(V_out), idx_out,
+                              static_cast<uint16_t*>(scores_out), d.H, d.S, d.D, d.n_kept, pl.P);
+}
+
+static bool choose_cluster(const Dims& d, ClusterPlan* pl) {
+    static const int knob_c = [] {  // A/B knob: cluster size (portable maximum 8); 0 disables the path
+        const char* v = getenv("KVP_KNORM_CLUSTER");
+        return (v && *v) ? atoi(v) : 8;
+    }();
+    if (knob_c <= 0 || d.R > 65535) return false;
+    int C = knob_c > 8 ? 8 : knob_c;
+    // few positions per row: a smaller cluster keeps every CTA busy
+    while (C > 1 && (d.S + C - 1) / C < 64) C >>= 1;
+    *pl = cluster_plan(d, C);
+    return pl->ok;
+}
+
+bool knorm_cluster_applicable(const Dims& d) {
+    ClusterPlan pl;
+    return choose_cluster(d, &pl);
+}
+
+// Returns cudaErrorNotSupported when the cache is too large for the cluster path (the caller takes the
+// multi-kernel path instead).
+cudaError_t launch_knorm_cluster(const Dims& d, int dtype, const void* K, const void* V, void* K_out, void* V_out,
+                                 int32_t* idx_out, void* scores_out, cudaStream_t st) {
+    ClusterPlan pl;
+    if (!choose_cluster(d, &pl)) return cudaErrorNotSupported;
+    const int nvec = d.D / 8;
+#define KVP_CL(LPR)                                                                                             \
+    return (dtype == KVP_BF16)                                                                                   \
+               ? launch_cluster_t<__nv_bfloat16, LPR>(d, pl, K, V, K_out, V_out, idx_out, scores_out, st)       \
+               : launch_cluster_t<__half, LPR>(d, pl, K, V, K_out, V_out, idx_out, scores_out, st)
+    if (nvec <= 4) KVP_CL(4);
+    if (nvec <= 8) KVP_CL(8);
+    if (nvec <= 16) KVP_CL(16);
+    KVP_CL(32);
+#undef KVP_CL
+}
+
+}  // namespace kvp

@@ -15,6 +15,7 @@
 //                    position order. Ties at T go to the lowest positions.
 // Tiles are visited in REVERSE order of the score stage so the K rows touched last (still in the
 // 126 MB L2) are re-read first.
+#include <stdlib.h>
 #include <type_traits>
 
 #include "common.cuh"
@@ -524,31 +525,43 @@ cudaError_t launch_select_compact_rerotate(const Dims& d, int dtype, const void*
 // Work items of three kinds share one ticket queue: S(row, chunk) scores 256 positions and adds to the
 // row histogram; A(row, group) is the refine item (waits until all S items of its row are done);
 // B(row, tile) is the compact item (waits for the row's ready flag). The queue is laid out in blocks
-//     block p = [ A(p-1) | S(p,0) B(p-2,0) S(p,1) B(p-2,1) ... ]
-// so that while row p is being scored (pure HBM reads), row p-2 is compacted: its K rows were read two
-// blocks ago (~2 x 32 MiB of traffic at 128k) and are re-read from the 126 MB L2 instead of HBM, its V
-// reads and all stores are L2-evict-first. Every item only waits on items that precede it in the
-// queue, and S items never wait, so the kernel cannot deadlock for any grid size.
+//     block p = [ A(p-1) | S(p, 0..m-1) | S(p, m..) evenly interleaved with B(p-lag, .) ]
+// so that while row p is being scored (pure HBM reads), row p-lag is compacted: its K rows were read `lag`
+// blocks ago and are re-read from the 126 MB L2 instead of HBM (V reads and all stores are L2-evict-first).
+// lag = 2, m = 0 (small caches): no compact item ever waits for a refine item of the same block.
+// lag = 1, m > 0 (large caches, K rows of one head = tens of MB): only two rows of K are live in L2; the m score
+// items in front of the first compact item give the row's refine items + scan time to finish.
+// Every item only waits on items that precede it in the queue, and S items never wait, so the kernel cannot
+// deadlock for any grid size.
 struct FusedItem {
     int kind;  // 0 = score, 1 = refine, 2 = compact, -1 = done
     int row, idx;
 };
 
-__device__ __forceinline__ FusedItem decode_fused_item(long long item, int R, int nT, int nA) {
+struct FusedQueue {
+    int R, nT, nA, lag, m_head;
+};
+
+__host__ __device__ __forceinline__ long long fused_total_items(const FusedQueue& q) {
+    return (long long)q.R * (2ll * q.nT + q.nA);
+}
+
+__host__ __device__ __forceinline__ FusedItem decode_fused_item(long long item, const FusedQueue& q) {
     FusedItem it = {-1, 0, 0};
-    for (int p = 0; p <= R + 1; ++p) {
-        // closed form over the identical middle blocks
-        if (p == 2 && R > 2) {
+    const int R = q.R, nT = q.nT, nA = q.nA, lag = q.lag;
+    for (int p = 0; p < R + lag; ++p) {
+        // closed form over the identical full blocks p in [lag, R)
+        if (p == lag && R > lag) {
             const long long full = (long long)nA + 2ll * nT;
-            const long long skip = item / full;
-            const long long n_mid = R - 2;
-            const long long take = skip < n_mid ? skip : n_mid;
-            item -= take * full;
-            p += (int)take;
+            const long long n_full = R - lag;
+            const long long skip = item / full < n_full ? item / full : n_full;
+            item -= skip * full;
+            p += (int)skip;
+            if (p >= R + lag) break;
         }
         const int a = (p >= 1 && p <= R) ? nA : 0;
         const int s = (p < R) ? nT : 0;
-        const int b = (p >= 2) ? nT : 0;
+        const int b = (p >= lag && p - lag < R) ? nT : 0;
         const long long size = (long long)a + s + b;
         if (item >= size) {
             item -= size;
@@ -559,17 +572,28 @@ __device__ __forceinline__ FusedItem decode_fused_item(long long item, int R, in
             return it;
         }
         const int j = (int)(item - a);
-        if (s && b) {
-            if (j & 1) { it.kind = 2; it.row = p - 2; it.idx = j >> 1; }
-            else       { it.kind = 0; it.row = p;     it.idx = j >> 1; }
-        } else if (s) {
+        const int mh = (s && b) ? (q.m_head < s ? q.m_head : s) : 0;  // score items in front of the mixed tail
+        if (j < mh || b == 0) {
             it.kind = 0; it.row = p; it.idx = j;
-        } else {
-            it.kind = 2; it.row = p - 2; it.idx = j;
+            return it;
         }
+        // tail: (s - mh) score items and b compact items, evenly interleaved (Bresenham)
+        const long long idx = j - mh, tail = (long long)(s - mh) + b;
+        const long long b_before = idx * b / tail, b_after = (idx + 1) * b / tail;
+        if (b_after != b_before) { it.kind = 2; it.row = p - lag; it.idx = (int)b_before; }
+        else                     { it.kind = 0; it.row = p;       it.idx = mh + (int)(idx - b_before); }
         return it;
     }
     return it;
+}
+
+// Host-side view of the queue for the CPU tests (tests/test_abi_symbols.py): item -> (kind, row, idx).
+extern "C" int kvp_debug_fused_queue_item(int R, int nT, int nA, int lag, int m_head, long long item, int* out3) {
+    const FusedQueue q = {R, nT, nA, lag, m_head};
+    if (item < 0 || item >= fused_total_items(q)) return -1;
+    const FusedItem it = decode_fused_item(item, q);
+    out3[0] = it.kind; out3[1] = it.row; out3[2] = it.idx;
+    return 0;
 }
 
 // Returns false when the wait was abandoned (error flag raised): the caller skips its item.
@@ -589,11 +613,12 @@ template <typename T, int LPR>
 __global__ void __launch_bounds__(kTileThreads, 3)
 knorm_fused_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks, Strides3 vs,
                    char* __restrict__ K_out, char* __restrict__ V_out, int32_t* __restrict__ idx_out,
-                   uint16_t* __restrict__ scores_out, int H, int S, int D, int n_kept, Workspace ws) {
+                   uint16_t* __restrict__ scores_out, int H, int S, int D, int n_kept, Workspace ws,
+                   FusedQueue fq, int k_evict_last) {
     __shared__ SelectSmem sm;
     const int R = ws.R, nT = ws.n_tiles;
-    const int nA = (nT + kGroupTiles - 1) / kGroupTiles;
-    const long long total = (long long)R * (2ll * nT + nA);
+    const int nA = fq.nA;
+    const long long total = fused_total_items(fq);
     uint32_t* score_done = ws.counters + kCounterMaxSlot(R) + 1;  // [R]
     uint16_t* skeys = reinterpret_cast<uint16_t*>(sm.list);       // 2 x 256 u16 alias the 1 KB list
     uint16_t* sscores = skeys + kScoreChunk;
@@ -604,10 +629,13 @@ knorm_fused_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks
         __syncthreads();
         const long long item = (long long)(uint32_t)sm.item;
         if (item >= total) break;
-        const FusedItem it = decode_fused_item(item, R, nT, nA);
+        const FusedItem it = decode_fused_item(item, fq);
         if (it.kind == 0) {
             sm.hist[tid] = 0;
-            knorm_score_chunk<T, LPR>(K, ks, it.row / H, it.row % H, it.idx, S, D, skeys, sscores);
+            if (k_evict_last)
+                knorm_score_chunk<T, LPR, true>(K, ks, it.row / H, it.row % H, it.idx, S, D, skeys, sscores);
+            else
+                knorm_score_chunk<T, LPR>(K, ks, it.row / H, it.row % H, it.idx, S, D, skeys, sscores);
             __syncthreads();
             flush_chunk_keys<1>(skeys, sscores, sm.hist, it.row, it.idx * kScoreChunk, S, ws, scores_out);
             __threadfence();
@@ -627,22 +655,42 @@ knorm_fused_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks
     }
 }
 
+// Debug / A-B knobs of the fused kernel's queue (read once): KVP_KNORM_FUSED_LAG = 1 | 2,
+// KVP_KNORM_FUSED_HEAD = percent of a row's score items in front of the mixed tail (lag 1),
+// KVP_KNORM_FUSED_KLAST = 1: score-stage K loads carry an L2 evict_last hint.
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 template <typename T>
 static cudaError_t launch_knorm_fused_t(const Dims& d, const void* K, const void* V, void* K_out,
                                         void* V_out, int32_t* idx_out, void* scores_out,
                                         const Workspace& ws, cudaStream_t st) {
-    const int nA = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
-    const long long total = (long long)d.R * (2ll * ws.n_tiles + nA);
+    static const int knob_lag = env_int("KVP_KNORM_FUSED_LAG", 0);
+    static const int knob_head = env_int("KVP_KNORM_FUSED_HEAD", 50);
+    static const int knob_klast = env_int("KVP_KNORM_FUSED_KLAST", -1);
+    FusedQueue fq;
+    fq.R = d.R;
+    fq.nT = ws.n_tiles;
+    fq.nA = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
+    // one kv-head row of K larger than ~8 MB: keep only two rows live in L2 (lag 1), else the latency-optimal lag 2
+    const bool big_rows = (size_t)d.S * d.D * 2 >= ((size_t)8 << 20);
+    fq.lag = (knob_lag == 1 || knob_lag == 2) ? knob_lag : (big_rows ? 1 : 2);
+    if (fq.lag > d.R) fq.lag = d.R;
+    fq.m_head = fq.lag == 1 ? (int)((long long)fq.nT * knob_head / 100) : 0;
+    const int k_last = knob_klast >= 0 ? knob_klast : (big_rows ? 1 : 0);
+    const long long total = fused_total_items(fq);
     if (total > 0x7FFFFFFFll) return cudaErrorNotSupported;
     const int nvec = d.D / 8;
 #define KVP_LAUNCH_FUSED(LPR)                                                                         \
     do {                                                                                              \
         auto kern = knorm_fused_kernel<T, LPR>;                                                       \
-        const int grid = persistent_grid(kern, kTileThreads, (int)total); \
+        const int grid = persistent_grid(kern, kTileThreads, (int)total);                             \
         kern<<<grid, kTileThreads, 0, st>>>(static_cast<const T*>(K), static_cast<const T*>(V), d.ks,  \
                                             d.vs, static_cast<char*>(K_out), static_cast<char*>(V_out), \
                                             idx_out, static_cast<uint16_t*>(scores_out), d.H, d.S, d.D, \
-                                            d.n_kept, ws);                                            \
+                                            d.n_kept, ws, fq, k_last);                                \
     } while (0)
     if (nvec <= 4) KVP_LAUNCH_FUSED(4);
     else if (nvec <= 8) KVP_LAUNCH_FUSED(8);

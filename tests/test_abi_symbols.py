@@ -134,3 +134,42 @@ def test_header_is_valid_c_and_links_from_c(tmp_path):
                    check=True, capture_output=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert out.startswith("abi 1 knorm_ws ")
+
+
+def test_fused_knorm_queue_is_a_valid_schedule():
+    """The item queue of the fused Knorm kernel (select_compact.cu: decode_fused_item) for both lags: every score /
+    refine / compact item appears exactly once, and every item comes after the items it waits for (refine(row) after
+    all score(row, .), compact(row, .) after all refine(row, .)) — the no-deadlock argument of the kernel."""
+    import ctypes
+
+    from kvpress_b200 import native
+
+    lib = ctypes.CDLL(str(native.library_path()))
+    fn = lib.kvp_debug_fused_queue_item
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int] * 5 + [ctypes.c_longlong, ctypes.POINTER(ctypes.c_int)]
+    out = (ctypes.c_int * 3)()
+    for R, nT, lag, m_head in [(8, 10, 2, 0), (1, 3, 1, 1), (1, 3, 2, 0), (2, 7, 2, 0), (8, 64, 1, 32), (3, 5, 1, 0),
+                               (5, 33, 1, 33), (4, 16, 1, 100), (2, 1, 1, 0), (9, 2, 2, 0)]:
+        lag = min(lag, R)
+        nA = (nT + 15) // 16
+        total = R * (2 * nT + nA)
+        seen, pos = set(), {}
+        for item in range(total):
+            assert fn(R, nT, nA, lag, m_head, item, out) == 0
+            key = (out[0], out[1], out[2])
+            assert key not in seen, (R, nT, lag, m_head, item, key)
+            seen.add(key)
+            pos[key] = item
+        assert fn(R, nT, nA, lag, m_head, total, out) == -1
+        want = {(0, r, i) for r in range(R) for i in range(nT)} | {(1, r, g) for r in range(R) for g in range(nA)} | \
+               {(2, r, i) for r in range(R) for i in range(nT)}
+        assert seen == want
+        for r in range(R):
+            last_score = max(pos[(0, r, i)] for i in range(nT))
+            first_refine, last_refine = min(pos[(1, r, g)] for g in range(nA)), max(pos[(1, r, g)] for g in range(nA))
+            first_compact = min(pos[(2, r, i)] for i in range(nT))
+            assert last_score < first_refine and last_refine < first_compact
+            if lag == 1 and r + 1 < R:  # the head of the next row's score items sits in front of the first compact item
+                head = min(m_head, nT)
+                assert all(pos[(0, r + 1, i)] < first_compact for i in range(head))

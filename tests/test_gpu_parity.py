@@ -86,6 +86,33 @@ def test_knorm_compress_vs_oracle_random(shape, ratio):
     assert O.check_selection(ref_scores, idx.cpu(), n_kept, ulp_slack=1)["ok"]
 
 
+@pytest.mark.parametrize("B,H,S,D", [(1, 8, 2560, 128), (1, 8, 4608, 128), (2, 3, 5119, 128), (1, 8, 2560, 64),
+                                     (1, 2, 700, 256), (1, 4, 65, 128), (1, 1, 7, 128), (3, 5, 512, 96)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_knorm_decoding_sized_caches(B, H, S, D, dtype):
+    """DecodingPress-sized compactions take the one-launch thread-block-cluster kernel (knorm_cluster.cu): the
+    configs[3] shapes 2560 -> 2048 and 4608 -> 2048, ragged slices, duplicate keys (forced ties at the threshold),
+    n_kept in {1, target, S}, strided views, no scratch involved."""
+    nat = _native()
+    torch.manual_seed(S * 7 + D)
+    wide = torch.randn(B, H, S + 9, D).to(dtype)
+    k = wide[:, :, 3:3 + S]                                    # a view: rows keep their stride, heads too
+    v = torch.randn(B, H, S, D).to(dtype)
+    if S > 40:
+        k[:, :, 20:30] = k[:, :, 5:15]                          # exact duplicates -> ties
+    kd, vd = wide.to(DEV)[:, :, 3:3 + S], v.to(DEV)
+    assert not kd.is_contiguous() or S == 0
+    for n_kept in sorted({1, min(S, 2048), max(1, S - S // 5), S}):
+        k_out, v_out, idx, scores = nat.knorm_compress(kd, vd, n_kept, return_indices=True, return_scores=True)
+        _check_compaction(k, v, k_out, v_out, idx)
+        assert ulp16_diff(scores.cpu(), O.knorm_scores(k.contiguous())).max() <= 1
+        assert torch.equal(idx.cpu().long(), O.select_lowest_index_ties(scores.cpu(), n_kept))
+        k2, v2, _, _ = nat.knorm_compress(kd, vd, n_kept)       # without the optional outputs
+        assert torch.equal(k2, k_out) and torch.equal(v2, v_out)
+    p = nat.make_problem(kd, vd, 1)
+    assert nat.launches_per_compress(p, 1) == 1                 # one launch, no memset node
+
+
 def test_knorm_full_size_properties():
     """BASELINE shape [1,8,131072,128]: size-independent properties instead of an element-wise oracle —
     highest-score-kept invariant (reference tests/presses/test_presses.py:143-162), exact gather,
