@@ -518,6 +518,12 @@ def expected_attention_compress(keys, values, mu, cov, epsilon: float, n_sink: i
 # generic scores (wrapper presses, user-defined ScorerPress subclasses)
 # --------------------------------------------------------------------------------------------------
 def scores_compress(scores: torch.Tensor, keys, values, n_kept: int, return_indices: bool = False):
+    """Top-k + compaction for caller-supplied scores [B, Hkv, S] (wrapper presses, user ScorerPress subclasses).
+
+    The selection kernels rank 16-bit keys: scores are compared IN THE CACHE DTYPE. The in-scope scorers return that
+    dtype already (as the reference's do); fp32 scores of a custom press are rounded to it first, so values that
+    differ only below bf16 / fp16 resolution become ties and go to the lowest positions, where the reference's fp32
+    `topk` would still order them."""
     _require_cuda_kv(keys, values)
     keys, values = _normalise(keys), _normalise(values)
     if tuple(scores.shape) != tuple(keys.shape[:3]) or scores.device != keys.device:

@@ -32,9 +32,23 @@ from kvpress_b200.utils import extract_keys_and_values
 logger = logging.getLogger(__name__)
 
 
+_RATIO_CACHE: dict = {}
+
+
 def find_target_compression_ratio(k_len: int, target: int, max_iterations: int = 20) -> float:
     """Ratio r with int(k_len * (1 - r)) == target, found by the reference's bisection
-    (decoding_press.py:194-236); 0.0 when the cache is already at or below the target."""
+    (decoding_press.py:194-236); 0.0 when the cache is already at or below the target. A decoding run asks for
+    the same two or three (k_len, target) pairs thousands of times (once per layer per compaction): memoised."""
+    key = (k_len, target, max_iterations)
+    hit = _RATIO_CACHE.get(key)
+    if hit is None:
+        if len(_RATIO_CACHE) > 4096:
+            _RATIO_CACHE.clear()
+        hit = _RATIO_CACHE[key] = _find_target_compression_ratio(k_len, target, max_iterations)
+    return hit
+
+
+def _find_target_compression_ratio(k_len: int, target: int, max_iterations: int = 20) -> float:
     if k_len <= target:
         return 0.0
     ratio = 1.0 - target / k_len

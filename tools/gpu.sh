@@ -1,11 +1,11 @@
 #!/bin/bash
 # tools/gpu.sh <timeout_s> [--gpus N] -- '<command>' : gpurun with retries while the pod has no free box (exit 3)
 t=$1; shift
-for attempt in $(seq 1 20); do
+for attempt in $(seq 1 60); do
   /usr/local/graft/bin/gpurun --timeout "$t" "$@"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
-  echo "[gpu.sh] no box (attempt $attempt), retrying in 150 s" >&2
-  sleep 150
+  echo "[gpu.sh] no box (attempt $attempt), retrying in 10 s" >&2
+  sleep 10
 done
 exit 3
