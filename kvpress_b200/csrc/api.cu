@@ -14,6 +14,9 @@ static thread_local char g_last_cuda_error[256] = "";
 static int fail_cuda(cudaError_t e) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", cudaGetErrorName(e),
              cudaGetErrorString(e));
+    // launch-configuration errors are not sticky: clear them, or the cudaPeekAtLastError() of every later call
+    // (of this library or of torch) would report this failure again
+    cudaGetLastError();
     return KVP_ERR_CUDA;
 }
 
@@ -177,7 +180,13 @@ int kvp_launches_per_compress(const kvp_problem* p, int scorer, int* launches_ou
         }
         case KVP_SCORER_KEYDIFF: *launches_out = 5; break;  // memset, anchor partials, merge, score, select+compact
         case KVP_SCORER_SNAPKV: *launches_out = 6; break;  // memset, stats, memset, colsum, finalize, select+compact
-        case KVP_SCORER_EXPECTED_ATTENTION: *launches_out = 5; break;  // memset, logits, vnorm (side stream), finalize, select+compact
+        case KVP_SCORER_EXPECTED_ATTENTION: {
+            // memset, triangular operand, logits (x2 above four heads per kv head), vnorm (side stream), finalize,
+            // select+compact (use_covariance + use_vnorm, the press defaults)
+            const int G = p->Hkv > 0 ? p->Hq / p->Hkv : 1;
+            *launches_out = 6 + (G > 4 ? 1 : 0);
+            break;
+        }
         default: return KVP_ERR_BAD_ARGUMENT;
     }
     return KVP_OK;

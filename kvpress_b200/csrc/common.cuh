@@ -235,30 +235,36 @@ __device__ __forceinline__ void flush_chunk_keys(const uint16_t* skeys, const ui
 // (DecodingPress compactions, per-layer prefill hooks).
 int device_sm_count();                         // SM count of the CURRENT device
 constexpr int kMaxDevices = 64;
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device). `done` is the CALLER's function-local
+// static (one per launcher instantiation): kernels that differ only in non-type template arguments share one function
+// POINTER TYPE, so a cache keyed on the template type of this helper would be shared between them.
+struct PerDeviceOnce {
+    unsigned long long mask = 0;  // bit per device; a lost race only repeats the idempotent call
+};
 template <typename Kern>
-static inline cudaError_t ensure_dynamic_smem(Kern kern, int bytes) {
-    static unsigned long long done = 0;  // bit per device; a lost race only repeats the idempotent call
+static inline cudaError_t ensure_dynamic_smem(Kern kern, int bytes, PerDeviceOnce& done) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < kMaxDevices && ((done >> dev) & 1ull)) return cudaSuccess;
+    if (dev >= 0 && dev < kMaxDevices && ((done.mask >> dev) & 1ull)) return cudaSuccess;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess && dev >= 0 && dev < kMaxDevices) done |= 1ull << dev;
+    if (e == cudaSuccess && dev >= 0 && dev < kMaxDevices) done.mask |= 1ull << dev;
     return e;
 }
-// resident CTAs per SM of a kernel (occupancy query) once per (kernel instantiation, device)
+// resident CTAs per SM of a kernel (occupancy query) once per (kernel, device); `cache` as above
+struct PerDeviceInt {
+    int v[kMaxDevices] = {0};
+};
 template <typename Kern>
-static inline int cached_ctas_per_sm(Kern kern, int threads, int dyn_smem = 0) {
-    static int cache[kMaxDevices] = {0};
+static inline int cached_ctas_per_sm(Kern kern, int threads, PerDeviceInt& cache, int dyn_smem = 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
-    if (cache[dev] == 0) {
+    if (cache.v[dev] == 0) {
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, dyn_smem);
-        cache[dev] = per_sm > 0 ? per_sm : 1;
+        cache.v[dev] = per_sm > 0 ? per_sm : 1;
     }
-    return cache[dev];
+    return cache.v[dev];
 }
 
 // ---- launchers implemented in the .cu files (host, C++ linkage) -------------------------------

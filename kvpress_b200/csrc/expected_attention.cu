@@ -691,18 +691,18 @@ cudaError_t launch_fill_sentinel(int dtype, void* scores_out, int R, int S, int 
 template <typename T>
 __global__ void __launch_bounds__(256)
 ea_cov_tri_kernel(const uint16_t* __restrict__ cov, uint16_t* __restrict__ tri, int D) {
-    const size_t base = (size_t)blockIdx.x * D * D;
-    for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
-        const int n = i / D, cidx = i - n * D;
-        uint16_t out = 0;
-        if (cidx == n) {
-            out = cov[base + i];
-        } else if (cidx < n) {
-            out = F16Traits<T>::from_float(F16Traits<T>::to_float(cov[base + i]) +
-                                           F16Traits<T>::to_float(cov[base + (size_t)cidx * D + n]));
-        }
-        tri[base + i] = out;
-    }
+    // one thread per element (it sits on the critical path in front of the logits kernel: two dependent-free loads,
+    // one store, thousands of CTAs instead of a per-head loop)
+    const size_t base = (size_t)blockIdx.y * D * D;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D * D) return;
+    const int n = i / D, cidx = i - n * D;
+    const uint16_t a = cov[base + i];
+    const uint16_t b = cov[base + (size_t)cidx * D + n];
+    uint16_t out = 0;
+    if (cidx == n) out = a;
+    else if (cidx < n) out = F16Traits<T>::from_float(F16Traits<T>::to_float(a) + F16Traits<T>::to_float(b));
+    tri[base + i] = out;
 }
 #endif
 
@@ -741,7 +741,8 @@ static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* 
         const void* cov_src = cov;
 #if KVP_EA_TRI
         if (g_off == 0) {  // (a second launch for the other four heads of a G = 8 group reuses it)
-            ea_cov_tri_kernel<T><<<d.B * d.Hq, 256, 0, st>>>(static_cast<const uint16_t*>(cov), sc.cov_tri, D);
+            ea_cov_tri_kernel<T><<<dim3((D * D + 255) / 256, d.B * d.Hq), 256, 0, st>>>(
+                static_cast<const uint16_t*>(cov), sc.cov_tri, D);
             cudaError_t pe = cudaPeekAtLastError();
             if (pe != cudaSuccess) return pe;
         }
@@ -752,7 +753,8 @@ static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* 
     }
     const int smem = L::kTotal + 1024;
     auto kern = ea_logits_kernel<T, D, G>;
-    cudaError_t e = ensure_dynamic_smem(kern, smem);
+    static PerDeviceOnce smem_set;  // one per <T, D, G> instantiation of this launcher
+    cudaError_t e = ensure_dynamic_smem(kern, smem, smem_set);
     if (e != cudaSuccess) return e;
     kern<<<grid, kEaThreads, smem, st>>>(mapK, mapCov, static_cast<const T*>(mu), d.H, d.Hq, d.S, n_sink, d.R,
                                          n_tiles128, ctas_per_row, ctas_per_row, sc, ws.S_pad, d.Hq / d.H, g_off);

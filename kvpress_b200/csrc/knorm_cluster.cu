@@ -268,7 +268,8 @@ template <typename T, int LPR>
 static cudaError_t launch_cluster_t(const Dims& d, const ClusterPlan& pl, const void* K, const void* V, void* K_out,
                                     void* V_out, int32_t* idx_out, void* scores_out, cudaStream_t st) {
     auto kern = knorm_cluster_kernel<T, LPR>;
-    cudaError_t e = ensure_dynamic_smem(kern, kClMaxSmem);
+    static PerDeviceOnce smem_set;  // one per <T, LPR> instantiation of this launcher
+    cudaError_t e = ensure_dynamic_smem(kern, kClMaxSmem, smem_set);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pl.C, d.R, 1);

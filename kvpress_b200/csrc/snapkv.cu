@@ -601,9 +601,10 @@ static cudaError_t launch_snap_t(const Dims& d, int dtype, const void* K, const 
     const int smem = L::kTotal + 1024;
     auto k1 = snap_stats_kernel<T, D, NQP>;
     auto k2 = snap_colsum_kernel<T, D, NQP>;
-    cudaError_t e = ensure_dynamic_smem(k1, smem);
+    static PerDeviceOnce smem_set1, smem_set2;  // one pair per <T, D, NQP> instantiation of this launcher
+    cudaError_t e = ensure_dynamic_smem(k1, smem, smem_set1);
     if (e != cudaSuccess) return e;
-    e = ensure_dynamic_smem(k2, smem);
+    e = ensure_dynamic_smem(k2, smem, smem_set2);
     if (e != cudaSuccess) return e;
 
     k1<<<grid, kSnThreads, smem, st>>>(mapK, mapQ, d.H, G, d.S, window, d.R, n_tiles128, ctas_per_row,
