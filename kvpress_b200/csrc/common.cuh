@@ -132,6 +132,30 @@ __device__ __forceinline__ void stg_hint(void* p, const int4& v, uint64_t pol) {
                  : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// The select+compact kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may
+// become resident while the LAST wave of the score / finalize kernel in front of it is still draining (that kernel
+// calls pdl_launch_dependents() at its start) and park in pdl_wait() until that grid has completed and flushed, so
+// the launch latency and the ramp of the persistent grid are off the critical path. Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- 256-bin suffix search, executed by ONE full warp ----------------------------------------
 // Finds the largest bin b with sum_{i>=b} hist[i] >= need (need >= 1) and returns
 // above = sum_{i>b} hist[i]. hist lives in shared memory. All 32 lanes get the result.

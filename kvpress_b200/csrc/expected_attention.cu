@@ -24,15 +24,16 @@
 #include "knorm_chunk.cuh"
 #include "umma.cuh"
 
-// Triangular quadratic form (default on). k^T cov k = sum_n k_n (sum_{c<=n} T[n][c] k_c) with
-// T[n][c] = cov[n][c] + cov[c][n] (c < n), cov[n][n] (c == n), 0 (c > n), built once per call by ea_cov_tri_kernel
-// into the scratch (exact whenever cov is symmetric, <= 2^-9 relative per entry otherwise: one rounding of the sum).
-// The B operand of K-step k (contraction columns c in [16k, 16k+16)) then has no non-zero rows n < 16k, so the MMA
-// warp issues that step on rows [32*(k/2), D) only: per head 2*(128+96+64+32) = 640 instead of 1024 N-units at
-// head_dim 128 (-37.5 % tensor cycles), 2*(64+32) = 192 instead of 256 at head_dim 64. KVP_EA_TRI=0 restores the
-// dense schedule (used by the A/B harness).
+// Triangular quadratic form — EXPERIMENT, default off (measured slower, profiles/r02_ab_ea_tri_hint.txt).
+// k^T cov k = sum_n k_n (sum_{c<=n} T[n][c] k_c) with T[n][c] = cov[n][c] + cov[c][n] (c < n), cov[n][n] (c == n),
+// 0 (c > n), built once per call by ea_cov_tri_kernel into the scratch (exact whenever cov is symmetric, <= 2^-9
+// relative per entry otherwise). The B operand of K-step k (contraction columns c in [16k, 16k+16)) then has no
+// non-zero rows n < 16k, so the MMA warp issues that step on rows [32*(k/2), D) only: per head 2*(128+96+64+32) = 640
+// instead of 1024 N-units at head_dim 128 (-37.5 % tensor work on paper). On the B200 the 15 narrower MMAs per
+// head pair (N = 256, 96, 64, 32) take LONGER than the 9 full-width ones: ea_logits_kernel 122 us vs 115 us, the
+// whole call 251 us vs 226 us. Parity-tested (all ExpectedAttention GPU tests pass with it on).
 #ifndef KVP_EA_TRI
-#define KVP_EA_TRI 1
+#define KVP_EA_TRI 0
 #endif
 
 namespace kvp {
@@ -575,6 +576,7 @@ ea_finalize_kernel(int G, int S, int n_sink, int use_vnorm, float eps, int n_par
     __shared__ float s_max[8];
     const int chunk = blockIdx.x, row = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     shist[tid] = 0;
+    pdl_launch_dependents();  // the select+compact kernel behind this one may start to take residency
     const int s0 = chunk * kEaFinalPos + tid * KPT;
     const bool in_pad = s0 < ws.S_pad;  // the padded scratch rows are readable up to S_pad (a multiple of 256)
     // 1. independent loads first: this thread's logits / norms and (warps < G) the per-CTA softmax partials
@@ -665,6 +667,7 @@ template <typename T>
 __global__ void fill_sentinel_kernel(uint16_t* __restrict__ scores_out, int R, int S, int lo, int hi,
                                      const uint32_t* __restrict__ max_slot) {
     const uint32_t ord = *max_slot;
+    pdl_launch_dependents();  // the select+compact kernel behind this one may start to take residency
     const uint32_t u = (ord & 0x80000000u) ? (ord & 0x7FFFFFFFu) : ~ord;
     const float sentinel = __uint_as_float(u) + 1.0f;
     const uint16_t bits = F16Traits<T>::from_float(sentinel);

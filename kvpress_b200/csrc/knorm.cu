@@ -20,6 +20,7 @@ knorm_score_kernel(const T* __restrict__ K, Strides3 ks, int H, int S, int D, Wo
     __shared__ uint32_t shist[256];
     const int chunk = blockIdx.x, row = blockIdx.y, tid = threadIdx.x;
     shist[tid] = 0;  // kTileThreads == 256
+    pdl_launch_dependents();  // the select+compact kernel behind this one may start to take residency
     knorm_score_chunk<T, LPR>(K, ks, row / H, row % H, chunk, S, D, skeys, sscores);
     __syncthreads();
     const int s_begin = chunk * kScoreChunk;
@@ -64,6 +65,7 @@ keys_from_scores_kernel(const uint16_t* __restrict__ scores, int64_t sb, int64_t
     const int tile = blockIdx.x, row = blockIdx.y, tid = threadIdx.x;
     const int b = row / H, h = row % H;
     shist[tid] = 0;
+    pdl_launch_dependents();  // the select+compact kernel behind this one may start to take residency
     const uint16_t* src = scores + (int64_t)b * sb + (int64_t)h * sh;
     const int s = tile * kTile + tid;
     skeys[tid] = (s < S) ? ordered_key16(src[s], inf_bits) : (uint16_t)0;

@@ -4,14 +4,15 @@
 //
 // At these sizes (tens of MB) the call is latency-bound: the multi-kernel path spends its time in launch gaps, a
 // memset node, global atomics and spin-waits between CTAs. Here one thread-block CLUSTER owns one (b, h) row:
-//   1. every CTA scores its slice of the row (128-bit loads, fp32 sum of squares, one rounding) and keeps the K rows
-//      it just read in shared memory;
+//   1. every CTA requests its whole slice of the row with cp.async up front — every K row, and every V row when both
+//      fit — so the slice is one memory round trip, then scores it from shared memory (fp32 sum of squares, one
+//      rounding);
 //   2. the 16-bit ordered keys of the slice are pushed into the shared memory of every CTA of the cluster
 //      (distributed shared memory), ONE cluster barrier;
 //   3. every CTA now holds the keys of the whole row and derives the exact threshold, the tie budget and the number
 //      of kept positions in front of its slice on its own (two 256-bin histograms + one counting pass);
-//   4. it ranks its slice and writes the kept K rows from shared memory and the kept V rows from global memory
-//      to their final places (ascending positions, ties to the lowest positions — same rule as select_compact.cu).
+//   4. it ranks its slice and writes the kept K (and V) rows from shared memory — V from global memory when it was
+//      not staged — to their final places (ascending positions, ties to the lowest positions — same rule as select_compact.cu).
 // No global atomics, no flags, no workspace: the only inter-CTA communication is the key exchange.
 #include <cooperative_groups.h>
 #include <stdlib.h>
@@ -28,6 +29,7 @@ constexpr int kClMaxSmem = 200 * 1024;  // K slice + keys of the row + lists mus
 struct ClusterPlan {
     int C;        // CTAs per cluster (= per row)
     int P;        // positions per CTA (multiple of 8)
+    int v_smem;   // 1: the V rows of the slice are staged in shared memory too (they fit)
     int smem;     // dynamic shared memory bytes
     bool ok;
 };
@@ -36,19 +38,29 @@ static ClusterPlan cluster_plan(const Dims& d, int C) {
     ClusterPlan pl;
     pl.C = C;
     pl.P = ((d.S + C - 1) / C + 7) / 8 * 8;
-    const size_t ktile = (size_t)pl.P * d.D * 2;
+    const size_t tile = (size_t)pl.P * d.D * 2;
     const size_t keys = (size_t)C * pl.P * 2;
     const size_t list = (size_t)pl.P * 4;
-    pl.smem = (int)(ktile + keys + list + 64);
+    pl.v_smem = (2 * tile + keys + list + 64 <= (size_t)kClMaxSmem) ? 1 : 0;
+    pl.smem = (int)((pl.v_smem ? 2 : 1) * tile + keys + list + 64);
     pl.ok = pl.smem <= kClMaxSmem;
     return pl;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 template <typename T, int LPR>
 __global__ void __launch_bounds__(kClThreads, 1)
 knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks, Strides3 vs,
                      char* __restrict__ K_out, char* __restrict__ V_out, int32_t* __restrict__ idx_out,
-                     uint16_t* __restrict__ scores_out, int H, int S, int D, int n_kept, int P) {
+                     uint16_t* __restrict__ scores_out, int H, int S, int D, int n_kept, int P, int v_smem) {
     extern __shared__ __align__(16) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
@@ -57,61 +69,73 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nvec = D >> 3;
 
-    int4* ktile = reinterpret_cast<int4*>(smem);                                        // [P][nvec] 16-byte pieces
-    uint16_t* all_keys = reinterpret_cast<uint16_t*>(smem + (size_t)P * D * 2);          // [C][P]
-    int* list = reinterpret_cast<int*>(smem + (size_t)P * D * 2 + (size_t)C * P * 2);    // [P] kept local positions
+    const size_t tile_bytes = (size_t)P * D * 2;
+    int4* ktile = reinterpret_cast<int4*>(smem);                                         // [P][nvec] 16-byte pieces
+    int4* vtile = reinterpret_cast<int4*>(smem + tile_bytes);                            // [P][nvec], only if v_smem
+    unsigned char* after = smem + (v_smem ? 2 : 1) * tile_bytes;
+    uint16_t* all_keys = reinterpret_cast<uint16_t*>(after);                             // [C][P]
+    int* list = reinterpret_cast<int*>(after + (size_t)C * P * 2);                       // [P] kept local positions
     __shared__ uint32_t hist[256];
     __shared__ uint32_t red[2][8];
     __shared__ uint32_t thr[4];
 
-    // all CTAs of the cluster have started (their shared memory exists) before anyone writes into it
-    cluster.sync();
-
-    // ---- 1. score this CTA's slice [start, start + P) and stage its K rows -------------------------------------
+    // ---- 1. stage the slice [start, start + P): every K row (and every V row when it fits) is requested up front
+    // with cp.async, so the whole slice is ONE memory round trip and costs no registers -----------------------------
     const int start = rank * P;
+    const int n_rows = max(0, min(P, S - start));
+    {
+        const char* k_src = reinterpret_cast<const char*>(K) + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2;
+        const char* v_src = reinterpret_cast<const char*>(V) + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2;
+        const int total = n_rows * nvec;
+        for (int i = tid; i < total; i += kClThreads) {
+            const int r = i / nvec, cc = i - r * nvec;
+            cp_async16(&ktile[i], k_src + (int64_t)(start + r) * ks.s * 2 + cc * 16);
+        }
+        if (v_smem)
+            for (int i = tid; i < total; i += kClThreads) {
+                const int r = i / nvec, cc = i - r * nvec;
+                cp_async16(&vtile[i], v_src + (int64_t)(start + r) * vs.s * 2 + cc * 16);
+            }
+    }
+    // all CTAs of the cluster have started (their shared memory exists) before anyone writes into it; the barrier
+    // overlaps the loads in flight
+    cluster.sync();
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---- score the slice from shared memory --------------------------------------------------------------------------
     uint16_t* my_keys = all_keys + (size_t)rank * P;
     {
         constexpr int RPW = 32 / LPR;
         constexpr int ROWS_PER_PASS = (kClThreads / 32) * RPW;
-        constexpr int U = 4;
         const int sub = lane % LPR, rsel = lane / LPR;
-        const T* base = K + (int64_t)b * ks.b + (int64_t)h * ks.h + (int64_t)sub * 8;
         const int n_pass = (P + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
-#pragma unroll 1
-        for (int j0 = 0; j0 < n_pass; j0 += U) {
-            int4 v[U];
+#pragma unroll 2
+        for (int j = 0; j < n_pass; ++j) {
+            const int r = j * ROWS_PER_PASS + warp * RPW + rsel;
+            const bool in_slice = r < P;
+            const bool valid = r < n_rows;
+            int4 v = make_int4(0, 0, 0, 0);
+            if (valid && sub < nvec) v = ktile[(size_t)r * nvec + sub];
+            const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+            float ss = 0.f;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int r = (j0 + u) * ROWS_PER_PASS + warp * RPW + rsel;
-                v[u] = make_int4(0, 0, 0, 0);
-                if (r < P && start + r < S && sub < nvec) v[u] = ldg_plain(base + (int64_t)(start + r) * ks.s);
+            for (int q = 0; q < 4; ++q) {
+                const float2 f = F16Traits<T>::unpack2(w[q]);
+                ss = fmaf(f.x, f.x, ss);
+                ss = fmaf(f.y, f.y, ss);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int r = (j0 + u) * ROWS_PER_PASS + warp * RPW + rsel;
-                const bool in_slice = r < P;
-                const bool valid = in_slice && start + r < S;
-                if (valid && sub < nvec) ktile[(size_t)r * nvec + sub] = v[u];
-                const uint32_t w[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z, (uint32_t)v[u].w};
-                float ss = 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = F16Traits<T>::unpack2(w[j]);
-                    ss = fmaf(f.x, f.x, ss);
-                    ss = fmaf(f.y, f.y, ss);
+            for (int off = LPR / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
+            if (sub == 0 && in_slice) {
+                uint16_t key = 0;
+                if (valid) {
+                    // -sqrt(ss) rounded once to the storage dtype (negation is exact): knorm_press.py:38
+                    const uint16_t bits = F16Traits<T>::from_float(sqrtf(ss)) ^ 0x8000u;
+                    key = ordered_key16(bits, F16Traits<T>::kInfBits);
+                    if (scores_out != nullptr) scores_out[(size_t)row * S + start + r] = bits;
                 }
-#pragma unroll
-                for (int off = LPR / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
-                if (sub == 0 && in_slice) {
-                    uint16_t key = 0;
-                    if (valid) {
-                        // -sqrt(ss) rounded once to the storage dtype (negation is exact): knorm_press.py:38
-                        const uint16_t bits = F16Traits<T>::from_float(sqrtf(ss)) ^ 0x8000u;
-                        key = ordered_key16(bits, F16Traits<T>::kInfBits);
-                        if (scores_out != nullptr) scores_out[(size_t)row * S + start + r] = bits;
-                    }
-                    my_keys[r] = key;
-                }
+                my_keys[r] = key;
             }
         }
     }
@@ -240,7 +264,16 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     char* v_dst = V_out + out_row0 * row_bytes;
     const uint64_t pol_first = l2_policy_evict_first();
     const int total = (int)count * nvec;
-    constexpr int UC = 4;
+    if (v_smem) {  // both tensors come from shared memory: pure stores
+        for (int i = tid; i < total; i += kClThreads) {
+            const int r = i / nvec, cc = i - r * nvec;
+            const int64_t off = (int64_t)r * row_bytes + cc * 16;
+            stg_hint(k_dst + off, ktile[(size_t)list[r] * nvec + cc], pol_first);
+            stg_hint(v_dst + off, vtile[(size_t)list[r] * nvec + cc], pol_first);
+        }
+        return;
+    }
+    constexpr int UC = 8;
     for (int base = tid; base < total; base += kClThreads * UC) {
         int4 vv[UC];
 #pragma unroll
@@ -285,7 +318,7 @@ static cudaError_t launch_cluster_t(const Dims& d, const ClusterPlan& pl, const 
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<const T*>(K), static_cast<const T*>(V), d.ks, d.vs,
                               static_cast<char*>(K_out), static_cast<char*>(V_out), idx_out,
-                              static_cast<uint16_t*>(scores_out), d.H, d.S, d.D, d.n_kept, pl.P);
+                              static_cast<uint16_t*>(scores_out), d.H, d.S, d.D, d.n_kept, pl.P, pl.v_smem);
 }
 
 static bool choose_cluster(const Dims& d, ClusterPlan* pl) {

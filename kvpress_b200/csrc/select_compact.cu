@@ -462,6 +462,7 @@ select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, St
     const int R = ws.R;
     const int n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
     const int nA = R * n_groups, nB = R * ws.n_tiles;
+    pdl_wait();  // keys + histograms of the score stage are complete and visible
     SEL_T0(t_kernel);
     while (true) {
         SEL_T0(t_ticket);
@@ -501,10 +502,16 @@ static cudaError_t launch_select_compact_t(const Dims& d, const void* K, const v
     auto kern = select_compact_kernel<TR>;
     static PerDeviceInt occupancy;  // one per <TR> instantiation of this launcher
     const int grid = persistent_grid(kern, kTileThreads, n_items, occupancy);
+#ifndef KVP_NO_PDL
+    return launch_pdl(kern, dim3(grid), dim3(kTileThreads), 0, st, static_cast<const char*>(K),
+                      static_cast<const char*>(V), d.ks, d.vs, static_cast<char*>(K_out), static_cast<char*>(V_out),
+                      idx_out, d.H, d.S, d.D, d.n_kept, ws, inv_freq);
+#else
     kern<<<grid, kTileThreads, 0, st>>>(static_cast<const char*>(K), static_cast<const char*>(V), d.ks, d.vs,
                                         static_cast<char*>(K_out), static_cast<char*>(V_out), idx_out, d.H,
                                         d.S, d.D, d.n_kept, ws, inv_freq);
     return cudaPeekAtLastError();
+#endif
 }
 
 cudaError_t launch_select_compact(const Dims& d, const void* K, const void* V, void* K_out,

@@ -1,7 +1,7 @@
 """Role-level wait/compute cycle counters of ea_logits_kernel (block 0), built with -DKVP_EA_PROFILE."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["KVPRESS_B200_LIB"] = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin", "libkvp_prof.so")
+os.environ["KVPRESS_B200_LIB"] = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin", "libv_prof.so")
 import torch
 from kvpress_b200 import native
 import bench
