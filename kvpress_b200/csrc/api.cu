@@ -181,10 +181,9 @@ int kvp_launches_per_compress(const kvp_problem* p, int scorer, int* launches_ou
         case KVP_SCORER_KEYDIFF: *launches_out = 5; break;  // memset, anchor partials, merge, score, select+compact
         case KVP_SCORER_SNAPKV: *launches_out = 6; break;  // memset, stats, memset, colsum, finalize, select+compact
         case KVP_SCORER_EXPECTED_ATTENTION: {
-            // memset, logits (x2 above four heads per kv head), vnorm (side stream), finalize, select+compact
-            // (use_covariance + use_vnorm, the press defaults; the KVP_EA_TRI experiment adds one)
-            const int G = p->Hkv > 0 ? p->Hq / p->Hkv : 1;
-            *launches_out = 5 + (G > 4 ? 1 : 0);
+            // memset, logits, vnorm (side stream), finalize, select+compact (use_covariance + use_vnorm, the press
+            // defaults; the KVP_EA_TRI experiment adds one)
+            *launches_out = 5;
             break;
         }
         default: return KVP_ERR_BAD_ARGUMENT;

@@ -36,6 +36,13 @@
 #define KVP_EA_TRI 0
 #endif
 
+// TIMING-ONLY experiment knobs (wrong results; used by tools/ea_experiments.py to locate the limiter of the logits
+// kernel): bit 0 = the epilogue does not read the k row from shared memory, bit 1 = no bias MMA step, bit 2 = the
+// epilogue does not read the accumulator at all (waits and releases only).
+#ifndef KVP_EA_EXP
+#define KVP_EA_EXP 0
+#endif
+
 namespace kvp {
 
 #ifdef KVP_EA_PROFILE
@@ -103,7 +110,11 @@ struct EaSmem {
     static constexpr int kCovHeadPanel = D * 128;          // bytes of one head's [D x 64] panel
     static constexpr int kCovBytes = G * kPanels * kCovHeadPanel;
     static constexpr int kStageBytes = kPanels * kEaTile * 128;
-    static constexpr int kStages = 2;
+    // K-tile ring: as deep as shared memory allows (4 when at most two heads' covariance is resident). With two
+    // stages a tile has ONE tile time to arrive after its slot is released; any extra HBM latency (the concurrent
+    // value-norm kernel) then starves the MMA pipe (profiles/r02_ea_experiments.txt).
+    static constexpr int kFixedBytes = kCovBytes + kEaTile * 32 + G * D * 32 + 512 + 1024;
+    static constexpr int kStages = (kFixedBytes + 4 * kStageBytes <= 227 * 1024) ? 4 : 2;
     static constexpr int kCovOff = 0;
     static constexpr int kStageOff = kCovBytes;
     // extra K=16 step that adds 2 sqrt(d) mu_g[n] to Y_g[.,n] inside the MMA: A-extra = [128 x 16]
@@ -121,7 +132,7 @@ template <typename T, int D, int G>
 __global__ void __launch_bounds__(512, 1)
 ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapCov,
                  const T* __restrict__ mu, int H, int Hq, int S, int n_sink, int R, int n_tiles128,
-                 int ctas_per_row, int n_parts, EaScratch sc, int S_pad, int g_total, int g_off) {
+                 int ctas_per_row, int n_parts, EaScratch sc, int S_pad, int g_total, int n_split) {
     using L = EaSmem<D, G>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // dynamic shared memory is only guaranteed 16-B aligned: round up to 1024 B for the swizzle
@@ -132,13 +143,14 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     unsigned char* s_ax = smem + L::kAxOff;
     unsigned char* s_bx = smem + L::kBxOff;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-    uint64_t* k_full = bars;         // [2]
-    uint64_t* k_empty = bars + 2;    // [2]
-    uint64_t* t_full = bars + 4;     // [2]
-    uint64_t* t_empty = bars + 6;    // [2]
-    uint64_t* cov_full = bars + 8;   // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-    float* s_red = reinterpret_cast<float*>(bars + 12);  // [8 warps][2 heads][2], then [2 wg][2][2]
+    constexpr int kStages = L::kStages;
+    uint64_t* k_full = bars;          // [kStages <= 4]
+    uint64_t* k_empty = bars + 4;     // [kStages]
+    uint64_t* t_full = bars + 8;      // [2]
+    uint64_t* t_empty = bars + 10;    // [2]
+    uint64_t* cov_full = bars + 12;   // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    float* s_red = reinterpret_cast<float*>(bars + 14);  // [8 warps][2 heads][2], then [2 wg][2][2]
 
     constexpr int kHalves = (G + 1) / 2;          // head pairs per tile
     constexpr int HPH = (G >= 2) ? 2 : 1;         // heads per half
@@ -160,9 +172,11 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     if (tid == 0) {
         umma::prefetch_tmap(&mapK);
         umma::prefetch_tmap(&mapCov);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kStages; ++i) {
             umma::mbar_init(&k_full[i], 1);
             umma::mbar_init(&k_empty[i], 1 + 8);  // MMA commit + 8 epilogue warps
+        }
+        for (int i = 0; i < 2; ++i) {
             umma::mbar_init(&t_full[i], 1);
             umma::mbar_init(&t_empty[i], 4);      // the 4 warps of the warpgroup that drained it
         }
@@ -186,9 +200,14 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     uint32_t h_it = 0;  // halves seen by this role
     uint32_t cov_it = 0;
 
-    for (int row = group; row < R; row += n_groups) {
+    // work unit = (row, group of G query heads of that kv head): the n_split units of a row run on different CTAs at the
+    // same time and stream the same K tiles (the second reader finds them in L2), each with only its own heads'
+    // covariance resident — which is what leaves room for the deeper K ring
+    const int n_units = R * n_split;
+    for (int unit = group; unit < n_units; unit += n_groups) {
+        const int row = unit / n_split, g_off = (unit % n_split) * G;
         const int b = row / H, h = row % H;
-        // this launch covers query heads [g_off, g_off + G) of the kv head's g_total heads
+        // this unit covers query heads [g_off, g_off + G) of the kv head's g_total heads
         const int hq0 = b * Hq + h * g_total + g_off;  // first of them in [B*Hq]
         __syncthreads();  // previous row fully drained (s_bias, s_cov, s_red reusable)
         for (int n = tid; n < G * D; n += kEaThreads) {
@@ -221,8 +240,8 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                         umma::tma_load_3d(s_cov + (kp * G + g) * L::kCovHeadPanel, &mapCov, cov_full,
                                           kp * 64, 0, hq0 + g);
                 for (int t = t_begin; t < t_end; ++t, ++k_it) {
-                    const int stage = k_it & 1;
-                    { EA_T0(); umma::mbar_wait(&k_empty[stage], ((k_it >> 1) & 1) ^ 1); EA_ACC(0); }
+                    const int stage = k_it % kStages;
+                    { EA_T0(); umma::mbar_wait(&k_empty[stage], ((k_it / kStages) & 1) ^ 1); EA_ACC(0); }
                     umma::mbar_arrive_expect_tx(&k_full[stage], L::kStageBytes);
                     for (int kp = 0; kp < L::kPanels; ++kp)
                         umma::tma_load_4d(s_stage + stage * L::kStageBytes + kp * (kEaTile * 128),
@@ -235,8 +254,8 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                 const uint32_t idesc = umma::instr_desc_f16(kEaTile, kN, F16Traits<T>::kMmaFormat);
                 umma::mbar_wait(cov_full, cov_it & 1);
                 for (int t = t_begin; t < t_end; ++t, ++k_it) {
-                    const int stage = k_it & 1;
-                    { EA_T0(); umma::mbar_wait(&k_full[stage], (k_it >> 1) & 1); EA_ACC(1); }
+                    const int stage = k_it % kStages;
+                    { EA_T0(); umma::mbar_wait(&k_full[stage], (k_it / kStages) & 1); EA_ACC(1); }
                     umma::fence_after_sync();
                     const uint32_t a_base = umma::smem_u32(s_stage + stage * L::kStageBytes);
 #pragma unroll 1
@@ -272,11 +291,13 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                                 umma::smem_u32(s_cov + (kp * G + half * HPH) * L::kCovHeadPanel) + kk * 32);
                             umma::mma_f16_ss(tmem + buf * kBufCols, da, db, idesc, k > 0);
                         }
+#if !(KVP_EA_EXP & 2)
                         umma::mma_f16_ss(tmem + buf * kBufCols,
                                          umma::smem_desc_k16_noswizzle(umma::smem_u32(s_ax)),
                                          umma::smem_desc_k16_noswizzle(
                                              umma::smem_u32(s_bx) + (half * HPH * D / 8) * 256),
                                          idesc, 1);
+#endif
                         umma::mma_commit(&t_full[buf]);
                     }
                     umma::mma_commit(&k_empty[stage]);
@@ -299,7 +320,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
             if (blockIdx.x == 0 && warp == 4 && lane == 0) g_ea_prof[9] += clock64() - t_entry;
 #endif
             for (int t = t_begin; t < t_end; ++t, ++k_it) {
-                const int stage = k_it & 1;
+                const int stage = k_it % kStages;
                 const unsigned char* krow = s_stage + stage * L::kStageBytes;
                 const int s = t * kEaTile + r;
                 const bool valid = (s >= n_sink) && (s < S);
@@ -310,7 +331,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     if (buf != wg) continue;
                     if (!waited_k) {
                         EA_T0();
-                        umma::mbar_wait(&k_full[stage], (k_it >> 1) & 1);
+                        umma::mbar_wait(&k_full[stage], (k_it / kStages) & 1);
                         if (warp == 4 && lane == 0) EA_ACC(3);
                         waited_k = true;
                     }
@@ -331,6 +352,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     // is in flight while step i is being reduced
                     constexpr int kC16 = D / 16;
                     uint32_t y[2][16];
+#if !(KVP_EA_EXP & 4)
                     umma::tmem_ld16(tbase, y[0]);
 #pragma unroll
                     for (int c = 0; c < kC16; ++c) {
@@ -341,9 +363,14 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                             const int kpanel = c0 >> 6;
 #pragma unroll
                             for (int ch = 0; ch < 2; ++ch) {
+#if KVP_EA_EXP & 1
+                                const uint4 v = make_uint4(0x3F803F80u + (uint32_t)(kpanel + ch), 0x3F803F80u, 0x3F803F80u,
+                                                           0x3F803F80u + (uint32_t)r);
+#else
                                 const uint4 v = *reinterpret_cast<const uint4*>(
                                     krow + kpanel * (kEaTile * 128) +
                                     umma::sw128_offset(r, ((c0 & 63) >> 3) + ch));
+#endif
                                 k2[ch * 4] = pack_f32x2(F16Traits<T>::unpack2(v.x));
                                 k2[ch * 4 + 1] = pack_f32x2(F16Traits<T>::unpack2(v.y));
                                 k2[ch * 4 + 2] = pack_f32x2(F16Traits<T>::unpack2(v.z));
@@ -365,6 +392,10 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                                 acc2[q][j & 3] = fma_f32x2(k2[j], pack_u32x2(yy[2 * j], yy[2 * j + 1]), acc2[q][j & 3]);
                         }
                     }
+#else
+                    (void)y;
+                    (void)krow;
+#endif
                     float acc[HPH];
 #pragma unroll
                     for (int q = 0; q < HPH; ++q) {
@@ -713,16 +744,20 @@ ea_cov_tri_kernel(const uint16_t* __restrict__ cov, uint16_t* __restrict__ tri, 
 template <typename T, int D, int G>
 static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* mu, const void* cov,
                                       int n_sink, const Workspace& ws, const EaScratch& sc,
-                                      int* n_parts_out, cudaStream_t st, int g_off = 0) {
+                                      int* n_parts_out, cudaStream_t st) {
     using L = EaSmem<D, G>;
     const int sm_count = device_sm_count();
     const int n_tiles128 = (d.S + kEaTile - 1) / kEaTile;
-    int ctas_per_row = sm_count / d.R;
+    // work units = (row, group of G heads); the CTAs of a unit split the row's tiles
+    const int g_total = d.Hq / d.H;
+    const int n_split = (g_total + G - 1) / G;
+    const int n_units = d.R * n_split;
+    int ctas_per_row = sm_count / n_units;  // CTAs per unit
     if (ctas_per_row < 1) ctas_per_row = 1;
     if (ctas_per_row > n_tiles128) ctas_per_row = n_tiles128;
     if (ctas_per_row > kEaMaxParts) ctas_per_row = kEaMaxParts;
     int n_groups = sm_count / ctas_per_row;
-    if (n_groups > d.R) n_groups = d.R;
+    if (n_groups > n_units) n_groups = n_units;
     const int grid = n_groups * ctas_per_row;
     *n_parts_out = ctas_per_row;
 
@@ -743,12 +778,10 @@ static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* 
         const uint32_t box[3] = {64, (uint32_t)D, 1};
         const void* cov_src = cov;
 #if KVP_EA_TRI
-        if (g_off == 0) {  // (a second launch for the other four heads of a G = 8 group reuses it)
-            ea_cov_tri_kernel<T><<<dim3((D * D + 255) / 256, d.B * d.Hq), 256, 0, st>>>(
-                static_cast<const uint16_t*>(cov), sc.cov_tri, D);
-            cudaError_t pe = cudaPeekAtLastError();
-            if (pe != cudaSuccess) return pe;
-        }
+        ea_cov_tri_kernel<T><<<dim3((D * D + 255) / 256, d.B * d.Hq), 256, 0, st>>>(
+            static_cast<const uint16_t*>(cov), sc.cov_tri, D);
+        cudaError_t pe = cudaPeekAtLastError();
+        if (pe != cudaSuccess) return pe;
         cov_src = sc.cov_tri;
 #endif
         cudaError_t e = make_tmap_16bit(&mapCov, cov_src, 3, dims, str, box);
@@ -760,7 +793,7 @@ static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* 
     cudaError_t e = ensure_dynamic_smem(kern, smem, smem_set);
     if (e != cudaSuccess) return e;
     kern<<<grid, kEaThreads, smem, st>>>(mapK, mapCov, static_cast<const T*>(mu), d.H, d.Hq, d.S, n_sink, d.R,
-                                         n_tiles128, ctas_per_row, ctas_per_row, sc, ws.S_pad, d.Hq / d.H, g_off);
+                                         n_tiles128, ctas_per_row, ctas_per_row, sc, ws.S_pad, g_total, n_split);
     return cudaPeekAtLastError();
 }
 
@@ -825,21 +858,24 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
         if ((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return e;
     }
     if (cov != nullptr) {
-        // tensor-core path: head_dim 64 or 128; 1, 2 or 4 query heads of a kv head resident in shared memory per
-        // launch. Other group sizes (3: Llama-3.2-3B, 5..8: Qwen2-7B has 7, Llama-3.1-70B 8) run on the 4-head
-        // instantiation with padding heads (no bias, nothing stored) and, above 4, a second launch for heads 4...
+        // tensor-core path: head_dim 64 or 128; the G query heads of a kv head are cut into groups of two (one for
+        // G = 1), each group is a work unit with its own covariance resident in shared memory; an odd G pads its last
+        // group with a head that has no bias and stores nothing (Llama-3.2-3B: 3, Qwen2-7B: 7, Llama-3.1-70B: 8).
         if (d.D != 128 && d.D != 64) return cudaErrorNotSupported;
         const bool d128 = d.D == 128;
+#ifndef KVP_EA_RESIDENT_HEADS
+#define KVP_EA_RESIDENT_HEADS 2  // A/B knob: 4 = round-1 layout (all four heads of a Llama-3.1-8B group in one CTA)
+#endif
         if (G == 1)
             e = d128 ? launch_ea_logits_t<T, 128, 1>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st)
                      : launch_ea_logits_t<T, 64, 1>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
-        else if (G == 2)
+        else if (G == 2 || KVP_EA_RESIDENT_HEADS == 2)
+            // two resident heads per CTA, ceil(G / 2) CTAs share a row's K tiles, 4-stage K ring
             e = d128 ? launch_ea_logits_t<T, 128, 2>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st)
                      : launch_ea_logits_t<T, 64, 2>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
         else
-            for (int g_off = 0; g_off < G && e == cudaSuccess; g_off += 4)
-                e = d128 ? launch_ea_logits_t<T, 128, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st, g_off)
-                         : launch_ea_logits_t<T, 64, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st, g_off);
+            e = d128 ? launch_ea_logits_t<T, 128, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st)
+                     : launch_ea_logits_t<T, 64, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
     } else {
         n_parts = (d.S + kScoreChunkGeneric - 1) / kScoreChunkGeneric;
         dim3 grid(n_parts, d.R);

@@ -10,7 +10,8 @@
 //   2. the 16-bit ordered keys of the slice are pushed into the shared memory of every CTA of the cluster
 //      (distributed shared memory), ONE cluster barrier;
 //   3. every CTA now holds the keys of the whole row and derives the exact threshold, the tie budget and the number
-//      of kept positions in front of its slice on its own (two 256-bin histograms + one counting pass);
+//      of kept positions in front of its slice on its own (a 17-step search over the threshold's bits: register-only
+//      counts + block reductions, no atomics);
 //   4. it ranks its slice and writes the kept K (and V) rows from shared memory — V from global memory when it was
 //      not staged — to their final places (ascending positions, ties to the lowest positions — same rule as select_compact.cu).
 // No global atomics, no flags, no workspace: the only inter-CTA communication is the key exchange.
@@ -24,6 +25,7 @@ namespace cg = cooperative_groups;
 namespace kvp {
 
 constexpr int kClThreads = 256;
+constexpr int kClMaxKeysPerThread = 24;  // keys of the row a thread holds in registers: S <= 256 * 24 = 6144
 constexpr int kClMaxSmem = 200 * 1024;  // K slice + keys of the row + lists must fit one CTA's shared memory
 
 struct ClusterPlan {
@@ -43,7 +45,7 @@ static ClusterPlan cluster_plan(const Dims& d, int C) {
     const size_t list = (size_t)pl.P * 4;
     pl.v_smem = (2 * tile + keys + list + 64 <= (size_t)kClMaxSmem) ? 1 : 0;
     pl.smem = (int)((pl.v_smem ? 2 : 1) * tile + keys + list + 64);
-    pl.ok = pl.smem <= kClMaxSmem;
+    pl.ok = pl.smem <= kClMaxSmem && d.S <= kClThreads * kClMaxKeysPerThread;
     return pl;
 }
 
@@ -75,9 +77,8 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     unsigned char* after = smem + (v_smem ? 2 : 1) * tile_bytes;
     uint16_t* all_keys = reinterpret_cast<uint16_t*>(after);                             // [C][P]
     int* list = reinterpret_cast<int*>(after + (size_t)C * P * 2);                       // [P] kept local positions
-    __shared__ uint32_t hist[256];
     __shared__ uint32_t red[2][8];
-    __shared__ uint32_t thr[4];
+    __shared__ uint32_t red3[2][3][8];
 
     // ---- 1. stage the slice [start, start + P): every K row (and every V row when it fits) is requested up front
     // with cp.async, so the whole slice is ONE memory round trip and costs no registers -----------------------------
@@ -139,7 +140,6 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
             }
         }
     }
-    hist[tid] = 0;
     __syncthreads();
 
     // ---- 2. all-gather of the keys through distributed shared memory ---------------------------------------------
@@ -155,69 +155,66 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     cluster.sync();  // release / acquire at cluster scope: every slice of all_keys is complete everywhere
 
     // ---- 3. exact threshold of the row, computed redundantly by every CTA -----------------------------------------
-    // position s of the row lives at all_keys[(s / P) * P + s % P] == all_keys[s] (slices are contiguous)
-    for (int s0 = 0; s0 < S; s0 += kClThreads) {  // uniform trip count: the warp votes below are full-mask
-        const int s = s0 + tid;
-        const unsigned bin = s < S ? (unsigned)(all_keys[s] >> 8) : 256u;
-        const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
-        if (bin < 256u && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
-    }
-    __syncthreads();
-    if (warp == 0) {
-        int b1;
-        uint32_t above1;
-        warp_suffix_find(hist, (uint32_t)n_kept, lane, b1, above1);
-        if (lane == 0) {
-            thr[0] = (uint32_t)b1;
-            thr[1] = (uint32_t)n_kept - above1;  // still needed from bin b1 (>= 1)
-        }
-    }
-    __syncthreads();
-    const unsigned b1 = thr[0];
-    const uint32_t need1 = thr[1];
-    hist[tid] = 0;
-    __syncthreads();
-    for (int s = tid; s < S; s += kClThreads) {
-        const unsigned k = all_keys[s];
-        if ((k >> 8) == b1) atomicAdd(&hist[k & 0xFF], 1u);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        int lo1;
-        uint32_t above2;
-        warp_suffix_find(hist, need1, lane, lo1, above2);
-        if (lane == 0) {
-            thr[2] = (b1 << 8) | (uint32_t)lo1;  // threshold key T
-            thr[3] = need1 - above2;             // ties (key == T) to take, lowest positions first
-        }
-    }
-    __syncthreads();
-    const uint32_t T16 = thr[2], n_take = thr[3];
-
-    // kept (> T) and tied (== T) positions in front of this CTA's slice
-    uint32_t gt_b = 0, eq_b = 0;
-    const int front = min(start, S);
-    for (int s = tid; s < front; s += kClThreads) {
-        const uint32_t k = all_keys[s];
-        gt_b += k > T16;
-        eq_b += k == T16;
-    }
+    // The whole row's keys sit in shared memory (position s at all_keys[s]: slices are contiguous); every thread takes
+    // the positions tid, tid + 256, ... into registers. The threshold T = the n_kept-th largest key is found by a
+    // 16-step search over its bits — T |= bit whenever at least n_kept keys are >= T | bit — each step one
+    // register-only count + one block reduction. No shared-memory atomics: Knorm scores of a row take ~100 distinct
+    // values, so histogram bins would be hammered by every warp at once (the first version of this kernel spent most
+    // of its time there).
+    uint32_t myk[kClMaxKeysPerThread];
+    const int n_mine = (S + kClThreads - 1) / kClThreads;  // <= kClMaxKeysPerThread (cluster_plan)
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        gt_b += __shfl_xor_sync(0xFFFFFFFFu, gt_b, off);
-        eq_b += __shfl_xor_sync(0xFFFFFFFFu, eq_b, off);
+    for (int i = 0; i < kClMaxKeysPerThread; ++i) {
+        const int s = i * kClThreads + tid;
+        myk[i] = (i < n_mine && s < S) ? (uint32_t)all_keys[s] + 1u : 0u;  // +1: 0 marks "no position", below any key
     }
-    if (lane == 0) {
-        red[0][warp] = gt_b;
-        red[1][warp] = eq_b;
-    }
-    __syncthreads();
-    uint32_t gt_before = 0, eq_before = 0;
+    auto block_sum3 = [&](uint32_t a, uint32_t b2, uint32_t c, int slot, uint32_t (&out)[3]) {
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        gt_before += red[0][w];
-        eq_before += red[1][w];
+        for (int off = 16; off >= 1; off >>= 1) {
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, off);
+            b2 += __shfl_xor_sync(0xFFFFFFFFu, b2, off);
+            c += __shfl_xor_sync(0xFFFFFFFFu, c, off);
+        }
+        if (lane == 0) {
+            red3[slot][0][warp] = a;
+            red3[slot][1][warp] = b2;
+            red3[slot][2][warp] = c;
+        }
+        __syncthreads();
+        out[0] = out[1] = out[2] = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            out[0] += red3[slot][0][w];
+            out[1] += red3[slot][1][w];
+            out[2] += red3[slot][2][w];
+        }
+    };
+    uint32_t T1 = 0;  // threshold in the shifted (+1) key space
+#pragma unroll 1
+    for (int bit = 16; bit >= 0; --bit) {  // shifted keys span 17 bits
+        const uint32_t cand = T1 | (1u << bit);
+        uint32_t c = 0;
+#pragma unroll
+        for (int i = 0; i < kClMaxKeysPerThread; ++i) c += myk[i] >= cand;
+        uint32_t tot[3];
+        block_sum3(c, 0u, 0u, bit & 1, tot);  // alternating slots: one barrier per step is enough
+        if (tot[0] >= (uint32_t)n_kept) T1 = cand;
     }
+    // kept (> T) positions of the row, and kept / tied positions in front of this CTA's slice
+    uint32_t n_gt = 0, gt_b = 0, eq_b = 0;
+#pragma unroll
+    for (int i = 0; i < kClMaxKeysPerThread; ++i) {
+        const bool front = (i * kClThreads + tid) < start;
+        n_gt += myk[i] > T1;
+        gt_b += front && myk[i] > T1;
+        eq_b += front && myk[i] == T1;
+    }
+    uint32_t tot[3];
+    __syncthreads();  // slot 0 was last read in the bit loop
+    block_sum3(n_gt, gt_b, eq_b, 0, tot);
+    const uint32_t T16 = T1 - 1u;                       // back to the 16-bit key space (T1 >= 1: n_kept >= 1)
+    const uint32_t n_take = (uint32_t)n_kept - tot[0];  // ties (key == T) to take, lowest positions first
+    const uint32_t gt_before = tot[1], eq_before = tot[2];
     __syncthreads();
 
     // ---- 4. rank the slice (position order) and copy the kept rows ------------------------------------------------
