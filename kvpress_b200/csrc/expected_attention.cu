@@ -113,13 +113,17 @@ struct EaSmem {
     // K-tile ring: as deep as shared memory allows (4 when at most two heads' covariance is resident). With two
     // stages a tile has ONE tile time to arrive after its slot is released; any extra HBM latency (the concurrent
     // value-norm kernel) then starves the MMA pipe (profiles/r02_ea_experiments.txt).
-    static constexpr int kFixedBytes = kCovBytes + kEaTile * 32 + G * D * 32 + 512 + 1024;
+    // V tiles (value norms computed inside this kernel): with at most two resident heads every tile leaves one epilogue
+    // warpgroup idle, and there is room for a 2-stage V ring staged by TMA next to the K ring
+    static constexpr int kVStages = (G <= 2) ? 2 : 0;
+    static constexpr int kFixedBytes = kCovBytes + kEaTile * 32 + G * D * 32 + 512 + 1024 + kVStages * kStageBytes;
     static constexpr int kStages = (kFixedBytes + 4 * kStageBytes <= 227 * 1024) ? 4 : 2;
     static constexpr int kCovOff = 0;
     static constexpr int kStageOff = kCovBytes;
     // extra K=16 step that adds 2 sqrt(d) mu_g[n] to Y_g[.,n] inside the MMA: A-extra = [128 x 16]
     // with columns 0,1 = 1.0; B-extra = [G*D x 16] with column 0/1 = hi/lo halves of the bias
-    static constexpr int kAxOff = kStageOff + kStages * kStageBytes;  // 128 rows * 32 B
+    static constexpr int kVStageOff = kStageOff + kStages * kStageBytes;
+    static constexpr int kAxOff = kVStageOff + kVStages * kStageBytes;  // 128 rows * 32 B
     static constexpr int kBxOff = kAxOff + kEaTile * 32;                // G*D rows * 32 B
     static constexpr int kBarOff = kBxOff + G * D * 32;
     static constexpr int kTotal = kBarOff + 512;
@@ -131,8 +135,9 @@ struct EaSmem {
 template <typename T, int D, int G>
 __global__ void __launch_bounds__(512, 1)
 ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapCov,
-                 const T* __restrict__ mu, int H, int Hq, int S, int n_sink, int R, int n_tiles128,
-                 int ctas_per_row, int n_parts, EaScratch sc, int S_pad, int g_total, int n_split) {
+                 const __grid_constant__ CUtensorMap mapV, const T* __restrict__ mu, int H, int Hq, int S, int n_sink,
+                 int R, int n_tiles128, int ctas_per_row, int n_parts, EaScratch sc, int S_pad, int g_total,
+                 int n_split, int do_vnorm) {
     using L = EaSmem<D, G>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // dynamic shared memory is only guaranteed 16-B aligned: round up to 1024 B for the swizzle
@@ -140,6 +145,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* s_cov = smem + L::kCovOff;
     unsigned char* s_stage = smem + L::kStageOff;
+    unsigned char* s_vstage = smem + L::kVStageOff;
     unsigned char* s_ax = smem + L::kAxOff;
     unsigned char* s_bx = smem + L::kBxOff;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -150,7 +156,10 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     uint64_t* t_empty = bars + 10;    // [2]
     uint64_t* cov_full = bars + 12;   // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-    float* s_red = reinterpret_cast<float*>(bars + 14);  // [8 warps][2 heads][2], then [2 wg][2][2]
+    uint64_t* v_full = bars + 14;     // [2]
+    uint64_t* v_empty = bars + 16;    // [2]
+    float* s_red = reinterpret_cast<float*>(bars + 18);  // [8 warps][2 heads][2], then [2 wg][2][2]
+    constexpr bool kInKernelV = L::kVStages > 0;
 
     constexpr int kHalves = (G + 1) / 2;          // head pairs per tile
     constexpr int HPH = (G >= 2) ? 2 : 1;         // heads per half
@@ -172,6 +181,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     if (tid == 0) {
         umma::prefetch_tmap(&mapK);
         umma::prefetch_tmap(&mapCov);
+        if (kInKernelV && do_vnorm) umma::prefetch_tmap(&mapV);
         for (int i = 0; i < kStages; ++i) {
             umma::mbar_init(&k_full[i], 1);
             umma::mbar_init(&k_empty[i], 1 + 8);  // MMA commit + 8 epilogue warps
@@ -179,6 +189,8 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         for (int i = 0; i < 2; ++i) {
             umma::mbar_init(&t_full[i], 1);
             umma::mbar_init(&t_empty[i], 4);      // the 4 warps of the warpgroup that drained it
+            umma::mbar_init(&v_full[i], 1);
+            umma::mbar_init(&v_empty[i], 4);      // the 4 warps of the warpgroup that took the norms
         }
         umma::mbar_init(cov_full, 1);
         umma::mbar_fence_init();
@@ -199,14 +211,18 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     uint32_t k_it = 0;  // tiles seen by this role
     uint32_t h_it = 0;  // halves seen by this role
     uint32_t cov_it = 0;
+    uint32_t v_it = 0;  // V tiles this CTA owns, seen by this role
 
     // work unit = (row, group of G query heads of that kv head): the n_split units of a row run on different CTAs at the
     // same time and stream the same K tiles (the second reader finds them in L2), each with only its own heads'
     // covariance resident — which is what leaves room for the deeper K ring
     const int n_units = R * n_split;
     for (int unit = group; unit < n_units; unit += n_groups) {
-        const int row = unit / n_split, g_off = (unit % n_split) * G;
+        const int row = unit / n_split, pair = unit % n_split, g_off = pair * G;
         const int b = row / H, h = row % H;
+        // the units of a row see the same tiles: unit `pair` also stages V and takes the value norms of the tiles
+        // t with t % n_split == pair
+        const bool v_active = kInKernelV && do_vnorm != 0;
         // this unit covers query heads [g_off, g_off + G) of the kv head's g_total heads
         const int hq0 = b * Hq + h * g_total + g_off;  // first of them in [B*Hq]
         __syncthreads();  // previous row fully drained (s_bias, s_cov, s_red reusable)
@@ -246,6 +262,15 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     for (int kp = 0; kp < L::kPanels; ++kp)
                         umma::tma_load_4d(s_stage + stage * L::kStageBytes + kp * (kEaTile * 128),
                                           &mapK, &k_full[stage], kp * 64, t * kEaTile, h, b);
+                    if (v_active && (t % n_split) == pair) {
+                        const int vs_i = v_it & 1;
+                        umma::mbar_wait(&v_empty[vs_i], ((v_it >> 1) & 1) ^ 1);
+                        umma::mbar_arrive_expect_tx(&v_full[vs_i], L::kStageBytes);
+                        for (int kp = 0; kp < L::kPanels; ++kp)
+                            umma::tma_load_4d(s_vstage + vs_i * L::kStageBytes + kp * (kEaTile * 128), &mapV,
+                                              &v_full[vs_i], kp * 64, t * kEaTile, h, b);
+                        ++v_it;
+                    }
                 }
             }
         } else if (warp == 1) {
@@ -325,6 +350,30 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                 const int s = t * kEaTile + r;
                 const bool valid = (s >= n_sink) && (s < S);
                 bool waited_k = false, released_k = false;
+                if (kInKernelV && v_active && (t % n_split) == pair) {
+                    // kHalves == 1: exactly one warpgroup has no accumulator to drain for this tile — it takes ||v||
+                    if ((int)(h_it & 1) != wg) {
+                        const int vs_i = v_it & 1;
+                        umma::mbar_wait(&v_full[vs_i], (v_it >> 1) & 1);
+                        const unsigned char* vrow = s_vstage + vs_i * L::kStageBytes;
+                        float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+                        for (int c8 = 0; c8 < D / 8; ++c8) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(
+                                vrow + (c8 >> 3) * (kEaTile * 128) + umma::sw128_offset(r, c8 & 7));
+                            const float2 f0 = F16Traits<T>::unpack2(v.x), f1 = F16Traits<T>::unpack2(v.y);
+                            const float2 f2 = F16Traits<T>::unpack2(v.z), f3 = F16Traits<T>::unpack2(v.w);
+                            ss0 = fmaf(f0.x, f0.x, ss0); ss1 = fmaf(f0.y, f0.y, ss1);
+                            ss0 = fmaf(f1.x, f1.x, ss0); ss1 = fmaf(f1.y, f1.y, ss1);
+                            ss0 = fmaf(f2.x, f2.x, ss0); ss1 = fmaf(f2.y, f2.y, ss1);
+                            ss0 = fmaf(f3.x, f3.x, ss0); ss1 = fmaf(f3.y, f3.y, ss1);
+                        }
+                        __syncwarp();
+                        if (lane == 0) umma::mbar_arrive(&v_empty[vs_i]);
+                        if (s < S) sc.vnorm[(size_t)row * S_pad + s] = sqrtf(ss0 + ss1);
+                    }
+                    ++v_it;
+                }
 #pragma unroll 1
                 for (int half = 0; half < kHalves; ++half, ++h_it) {
                     const int buf = h_it & 1;
@@ -742,8 +791,8 @@ ea_cov_tri_kernel(const uint16_t* __restrict__ cov, uint16_t* __restrict__ tri, 
 
 // ---- host launcher -----------------------------------------------------------------------------------
 template <typename T, int D, int G>
-static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* mu, const void* cov,
-                                      int n_sink, const Workspace& ws, const EaScratch& sc,
+static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* V_or_null, const void* mu,
+                                      const void* cov, int n_sink, const Workspace& ws, const EaScratch& sc,
                                       int* n_parts_out, cudaStream_t st) {
     using L = EaSmem<D, G>;
     const int sm_count = device_sm_count();
@@ -761,7 +810,20 @@ static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* 
     const int grid = n_groups * ctas_per_row;
     *n_parts_out = ctas_per_row;
 
-    CUtensorMap mapK, mapCov;
+    CUtensorMap mapK, mapCov, mapV;
+    const bool in_kernel_v = L::kVStages > 0 && V_or_null != nullptr;
+    {  // V tiles are staged exactly like K tiles (same box, same swizzle), from V's own strides
+        const void* base = in_kernel_v ? V_or_null : K;
+        const Strides3& xs = in_kernel_v ? d.vs : d.ks;
+        const uint64_t row_b = (uint64_t)xs.s * 2;
+        const uint64_t h_b = d.H > 1 ? (uint64_t)xs.h * 2 : row_b * (uint64_t)d.S;
+        const uint64_t b_b = d.B > 1 ? (uint64_t)xs.b * 2 : h_b * (uint64_t)d.H;
+        const uint64_t dims[4] = {(uint64_t)D, (uint64_t)d.S, (uint64_t)d.H, (uint64_t)d.B};
+        const uint64_t str[4] = {0, row_b, h_b, b_b};
+        const uint32_t box[4] = {64, (uint32_t)kEaTile, 1, 1};
+        cudaError_t e = make_tmap_16bit(&mapV, base, 4, dims, str, box);
+        if (e != cudaSuccess) return e;
+    }
     {
         const uint64_t row_b = (uint64_t)d.ks.s * 2;
         const uint64_t h_b = d.H > 1 ? (uint64_t)d.ks.h * 2 : row_b * (uint64_t)d.S;
@@ -792,8 +854,9 @@ static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* 
     static PerDeviceOnce smem_set;  // one per <T, D, G> instantiation of this launcher
     cudaError_t e = ensure_dynamic_smem(kern, smem, smem_set);
     if (e != cudaSuccess) return e;
-    kern<<<grid, kEaThreads, smem, st>>>(mapK, mapCov, static_cast<const T*>(mu), d.H, d.Hq, d.S, n_sink, d.R,
-                                         n_tiles128, ctas_per_row, ctas_per_row, sc, ws.S_pad, g_total, n_split);
+    kern<<<grid, kEaThreads, smem, st>>>(mapK, mapCov, mapV, static_cast<const T*>(mu), d.H, d.Hq, d.S, n_sink, d.R,
+                                         n_tiles128, ctas_per_row, ctas_per_row, sc, ws.S_pad, g_total, n_split,
+                                         in_kernel_v ? 1 : 0);
     return cudaPeekAtLastError();
 }
 
@@ -847,8 +910,17 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
     const EaScratch sc = carve_ea(d, ws);
     int n_parts = 0;
     cudaError_t e = cudaSuccess;
-    // fork: the V-norm kernel only needs V; it runs on the side stream next to the logits kernel
-    EaSideStream* side = use_vnorm ? ea_side_stream() : nullptr;
+    // Value norms: with covariance and at most two resident heads per CTA (the default layout) the logits kernel stages
+    // the V tiles itself and an idle epilogue warpgroup takes the norms — no second kernel. Otherwise (covariance-free
+    // scan, or the four-head A/B layout) ea_vnorm_kernel runs on an internal side stream next to the score kernel:
+    // fork here, join before the finalize kernel.
+#ifndef KVP_EA_RESIDENT_HEADS
+#define KVP_EA_RESIDENT_HEADS 2  // A/B knob: 4 = round-1 layout (all four heads of a Llama-3.1-8B group in one CTA)
+#endif
+    const bool tc_path = cov != nullptr && (d.D == 128 || d.D == 64);
+    const bool in_kernel_v = use_vnorm && tc_path && (G <= 2 || KVP_EA_RESIDENT_HEADS == 2);
+    const void* v_for_logits = in_kernel_v ? V : nullptr;
+    EaSideStream* side = (use_vnorm && !in_kernel_v) ? ea_side_stream() : nullptr;
     // host threads enqueueing on different streams of one device share the side stream and its two
     // events: hold the lock for the (host-only, microseconds) fork..join enqueue sequence
     std::unique_lock<std::mutex> enqueue_lock(g_ea_enqueue_mu, std::defer_lock);
@@ -863,19 +935,16 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
         // group with a head that has no bias and stores nothing (Llama-3.2-3B: 3, Qwen2-7B: 7, Llama-3.1-70B: 8).
         if (d.D != 128 && d.D != 64) return cudaErrorNotSupported;
         const bool d128 = d.D == 128;
-#ifndef KVP_EA_RESIDENT_HEADS
-#define KVP_EA_RESIDENT_HEADS 2  // A/B knob: 4 = round-1 layout (all four heads of a Llama-3.1-8B group in one CTA)
-#endif
         if (G == 1)
-            e = d128 ? launch_ea_logits_t<T, 128, 1>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st)
-                     : launch_ea_logits_t<T, 64, 1>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
+            e = d128 ? launch_ea_logits_t<T, 128, 1>(d, K, v_for_logits, mu, cov, n_sink, ws, sc, &n_parts, st)
+                     : launch_ea_logits_t<T, 64, 1>(d, K, v_for_logits, mu, cov, n_sink, ws, sc, &n_parts, st);
         else if (G == 2 || KVP_EA_RESIDENT_HEADS == 2)
-            // two resident heads per CTA, ceil(G / 2) CTAs share a row's K tiles, 4-stage K ring
-            e = d128 ? launch_ea_logits_t<T, 128, 2>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st)
-                     : launch_ea_logits_t<T, 64, 2>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
+            // two resident heads per CTA, ceil(G / 2) CTAs share a row's K tiles
+            e = d128 ? launch_ea_logits_t<T, 128, 2>(d, K, v_for_logits, mu, cov, n_sink, ws, sc, &n_parts, st)
+                     : launch_ea_logits_t<T, 64, 2>(d, K, v_for_logits, mu, cov, n_sink, ws, sc, &n_parts, st);
         else
-            e = d128 ? launch_ea_logits_t<T, 128, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st)
-                     : launch_ea_logits_t<T, 64, 4>(d, K, mu, cov, n_sink, ws, sc, &n_parts, st);
+            e = d128 ? launch_ea_logits_t<T, 128, 4>(d, K, nullptr, mu, cov, n_sink, ws, sc, &n_parts, st)
+                     : launch_ea_logits_t<T, 64, 4>(d, K, nullptr, mu, cov, n_sink, ws, sc, &n_parts, st);
     } else {
         n_parts = (d.S + kScoreChunkGeneric - 1) / kScoreChunkGeneric;
         dim3 grid(n_parts, d.R);
@@ -891,7 +960,7 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
         e = cudaPeekAtLastError();
     }
     if (e != cudaSuccess) return e;
-    if (use_vnorm) {
+    if (use_vnorm && !in_kernel_v) {
         // launched AFTER the logits kernel so that its CTAs fill the resources the logits CTAs leave free
         cudaStream_t vst = side != nullptr ? side->stream : st;
         if ((e = launch_ea_vnorm_t<T>(d, V, ws, sc, vst)) != cudaSuccess) return e;

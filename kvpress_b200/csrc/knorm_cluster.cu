@@ -24,6 +24,22 @@ namespace cg = cooperative_groups;
 
 namespace kvp {
 
+#ifdef KVP_CL_PROFILE
+// phase timestamps (globaltimer, ns) of CTA (0, 0), thread 0: tools/cluster_profile.py
+__device__ unsigned long long g_cl_prof[16];
+__device__ __forceinline__ unsigned long long cl_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define CL_MARK(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_cl_prof[i] = cl_now(); } while (0)
+extern "C" void kvp_debug_cluster_profile(unsigned long long* out) {
+    cudaMemcpyFromSymbol(out, g_cl_prof, 16 * sizeof(unsigned long long));
+}
+#else
+#define CL_MARK(i) do {} while (0)
+#endif
+
 constexpr int kClThreads = 256;
 constexpr int kClMaxKeysPerThread = 24;  // keys of the row a thread holds in registers: S <= 256 * 24 = 6144
 constexpr int kClMaxSmem = 200 * 1024;  // K slice + keys of the row + lists must fit one CTA's shared memory
@@ -84,6 +100,7 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     // with cp.async, so the whole slice is ONE memory round trip and costs no registers -----------------------------
     const int start = rank * P;
     const int n_rows = max(0, min(P, S - start));
+    CL_MARK(0);
     {
         const char* k_src = reinterpret_cast<const char*>(K) + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2;
         const char* v_src = reinterpret_cast<const char*>(V) + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2;
@@ -100,9 +117,12 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     }
     // all CTAs of the cluster have started (their shared memory exists) before anyone writes into it; the barrier
     // overlaps the loads in flight
+    CL_MARK(1);
     cluster.sync();
+    CL_MARK(2);
     cp_async_wait_all();
     __syncthreads();
+    CL_MARK(3);
 
     // ---- score the slice from shared memory --------------------------------------------------------------------------
     uint16_t* my_keys = all_keys + (size_t)rank * P;
@@ -141,6 +161,7 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
         }
     }
     __syncthreads();
+    CL_MARK(4);
 
     // ---- 2. all-gather of the keys through distributed shared memory ---------------------------------------------
     {
@@ -152,7 +173,9 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
             for (int i = tid; i < n8; i += kClThreads) dst[i] = src[i];
         }
     }
+    CL_MARK(5);
     cluster.sync();  // release / acquire at cluster scope: every slice of all_keys is complete everywhere
+    CL_MARK(6);
 
     // ---- 3. exact threshold of the row, computed redundantly by every CTA -----------------------------------------
     // The whole row's keys sit in shared memory (position s at all_keys[s]: slices are contiguous); every thread takes
@@ -217,6 +240,7 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     const uint32_t gt_before = tot[1], eq_before = tot[2];
     __syncthreads();
 
+    CL_MARK(7);
     // ---- 4. rank the slice (position order) and copy the kept rows ------------------------------------------------
     uint32_t taken_eq = min(eq_before, n_take);  // ties already granted to lower positions
     const uint32_t out_base = gt_before + taken_eq;
@@ -251,6 +275,7 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
         taken_eq += took;
         __syncthreads();
     }
+    CL_MARK(8);
     if (count == 0) return;
     const int64_t out_row0 = (int64_t)row * n_kept + out_base;
     if (idx_out != nullptr)
@@ -268,6 +293,7 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
             stg_hint(k_dst + off, ktile[(size_t)list[r] * nvec + cc], pol_first);
             stg_hint(v_dst + off, vtile[(size_t)list[r] * nvec + cc], pol_first);
         }
+        CL_MARK(9);
         return;
     }
     constexpr int UC = 8;

@@ -27,6 +27,24 @@
 
 namespace kvp {
 
+#ifdef KVP_SNAP_PROFILE
+// role-level cycle counters of CTA 0 of snap_stats_kernel (tools/snap_profile.py)
+__device__ long long g_snap_prof[16];
+#define SN_T0() const long long _t0 = clock64()
+#define SN_ACC(slot) do { if (blockIdx.x == 0) g_snap_prof[slot] += clock64() - _t0; } while (0)
+extern "C" void kvp_debug_snap_profile(long long* out, int reset) {
+    if (reset) {
+        long long z[16] = {0};
+        cudaMemcpyToSymbol(g_snap_prof, z, sizeof(z));
+    } else {
+        cudaMemcpyFromSymbol(out, g_snap_prof, 16 * sizeof(long long));
+    }
+}
+#else
+#define SN_T0() do {} while (0)
+#define SN_ACC(slot) do {} while (0)
+#endif
+
 constexpr int kSnTile = 128;
 constexpr int kSnThreads = 640;  // 20 warps: TMA, MMA, TMEM-alloc, spare, 4 x 4 epilogue (2 warpgroups per TMEM buffer)
 constexpr int kSnMaxParts = 640;
@@ -152,7 +170,7 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
                                           q_row0 + r0, 0);
                 for (int t = t_begin; t < t_end; ++t, ++k_it) {
                     const int stage = k_it & 1;
-                    umma::mbar_wait(&k_empty[stage], ((k_it >> 1) & 1) ^ 1);
+                    { SN_T0(); umma::mbar_wait(&k_empty[stage], ((k_it >> 1) & 1) ^ 1); SN_ACC(0); }
                     umma::mbar_arrive_expect_tx(&k_full[stage], L::kStageBytes);
                     for (int kp = 0; kp < L::kPanels; ++kp)
                         umma::tma_load_4d(s_stage + stage * L::kStageBytes + kp * (kSnTile * 128), &mapK,
@@ -165,13 +183,13 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
                 umma::mbar_wait(q_full, q_it & 1);
                 for (int t = t_begin; t < t_end; ++t, ++k_it) {
                     const int stage = k_it & 1;
-                    umma::mbar_wait(&k_full[stage], (k_it >> 1) & 1);
+                    { SN_T0(); umma::mbar_wait(&k_full[stage], (k_it >> 1) & 1); SN_ACC(1); }
                     umma::fence_after_sync();
                     const uint32_t kb = umma::smem_u32(s_stage + stage * L::kStageBytes);
 #pragma unroll 1
                     for (int qh = 0; qh < kQHalves; ++qh, ++h_it) {
                         const int buf = h_it & 1;
-                        umma::mbar_wait(&t_empty[buf], ((h_it >> 1) & 1) ^ 1);
+                        { SN_T0(); umma::mbar_wait(&t_empty[buf], ((h_it >> 1) & 1) ^ 1); SN_ACC(2); }
                         umma::fence_after_sync();
 #pragma unroll
                         for (int k = 0; k < D / 16; ++k) {
@@ -213,7 +231,8 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
                     const int slot = qh >> 1;
                     const int r = qh * 128 + ew * 32 + lane;       // query row
                     const int limit = (S - window) + (r % window);  // last visible key position
-                    umma::mbar_wait(&t_full[buf], (h_it >> 1) & 1);
+                    { SN_T0(); umma::mbar_wait(&t_full[buf], (h_it >> 1) & 1); if (warp == 4 && lane == 0) SN_ACC(3); }
+                    SN_T0();
                     umma::fence_after_sync();
                     const uint32_t tbase = tmem + lane_base + buf * kBufCols + ch * kHalfCols;
                     uint32_t y[2][16];
@@ -271,6 +290,7 @@ snap_stats_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
                     }
                     run_m[slot] = m;
                     run_z[slot] = z;
+                    if (warp == 4 && lane == 0) SN_ACC(4);
                     umma::fence_before_sync();
                     __syncwarp();
                     if (lane == 0) umma::mbar_arrive(&t_empty[buf]);
