@@ -100,6 +100,15 @@ def algorithmic_flops(w: dict) -> float:
     return 0.0
 
 
+def mufu_bound_us(w: dict) -> float:
+    """SnapKV's exact softmax costs two exponentials per (window query, key): pass 1 for the normalisers, pass 2 for the
+    normalised column sums. MUFU.EX2 issues 16 per clock per SM; packed f16x2 / bf16x2 forms compile to two MUFU ops on
+    sm_100a, so this is a hard floor of the exact two-pass algorithm: 2 * w * Hq * S exps / (16 * 148 SMs * 1.965 GHz)."""
+    if w["scorer"] != "snapkv":
+        return 0.0
+    return 2.0 * 64 * w["B"] * w["Hq"] * w["S"] / (16.0 * 148 * 1.965e9) * 1e6
+
+
 def load_traffic(workload: str):
     """DRAM bytes one compress call moves (sum over its kernels, dram__bytes_read + write per launch) from the
     committed ncu launch list of the same command: profiles/traffic.json, written by tools/ncu_launches.py."""
@@ -460,6 +469,10 @@ def extra_workload(name: str, device, rank: int, steps: int, peaks: dict) -> dic
     if flops:
         out["tensor_bound_us"] = flops / (peaks["bf16_tflops_sustained"] * 1e12) * 1e6
         out["hbm_bound_us"] = abytes / (peaks["hbm_gbs"] * 1e9) * 1e6
+    if mufu_bound_us(w):
+        out["mufu_bound_us"] = mufu_bound_us(w)
+        out["frac_of_binding_roof"] = max(out.get("hbm_bound_us", 0.0), out.get("tensor_bound_us", 0.0),
+                                          out["mufu_bound_us"]) / (ms * 1e3)
     del graphs, sets
     torch.cuda.empty_cache()
     return out
@@ -758,6 +771,9 @@ def main():
         # lower bound on the tensor-core rate of the score stage: all of the step time charged to it
         roofline["tensor"] = {"algorithmic_flops_per_launch": flops, "achieved_tflops_lower_bound": flops / (ms_per_step * 1e-3) / 1e12,
                               "peak_tflops": peaks["bf16_tflops"], "unit": "TFLOP/s"}
+    if mufu_bound_us(w):
+        roofline["mufu"] = {"bound_us": mufu_bound_us(w), "frac": mufu_bound_us(w) / (ms_per_step * 1e3),
+                            "note": "two exact-softmax passes, 16 MUFU.EX2 / clk / SM"}
 
     # ---------------- e2e: pinned host K/V in, compacted K'/V' out, through the host-buffer API ---------
     e2e = None

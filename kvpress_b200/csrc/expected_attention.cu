@@ -115,9 +115,15 @@ struct EaSmem {
     // value-norm kernel) then starves the MMA pipe (profiles/r02_ea_experiments.txt).
     // V tiles (value norms computed inside this kernel): with at most two resident heads every tile leaves one epilogue
     // warpgroup idle, and there is room for a 2-stage V ring staged by TMA next to the K ring
-    static constexpr int kVStages = (G <= 2) ? 2 : 0;
+#ifndef KVP_EA_V_STAGES
+#define KVP_EA_V_STAGES 1  // A/B knob: 0 = value norms by the side-stream kernel, 1 / 2 = V ring depth inside this kernel
+#endif
+    static constexpr int kVStages = (G <= 2) ? KVP_EA_V_STAGES : 0;
     static constexpr int kFixedBytes = kCovBytes + kEaTile * 32 + G * D * 32 + 512 + 1024 + kVStages * kStageBytes;
-    static constexpr int kStages = (kFixedBytes + 4 * kStageBytes <= 227 * 1024) ? 4 : 2;
+    // as many K stages as fit, at most 4 (two units per row halve the tile time of a CTA: run6 measured the two-head
+    // layout at 154 us with 2 stages against 116 us with 4)
+    static constexpr int kFit = (227 * 1024 - kFixedBytes) / kStageBytes;
+    static constexpr int kStages = kFit >= 4 ? 4 : (kFit >= 2 ? kFit : 2);
     static constexpr int kCovOff = 0;
     static constexpr int kStageOff = kCovBytes;
     // extra K=16 step that adds 2 sqrt(d) mu_g[n] to Y_g[.,n] inside the MMA: A-extra = [128 x 16]
@@ -263,8 +269,9 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                         umma::tma_load_4d(s_stage + stage * L::kStageBytes + kp * (kEaTile * 128),
                                           &mapK, &k_full[stage], kp * 64, t * kEaTile, h, b);
                     if (v_active && (t % n_split) == pair) {
-                        const int vs_i = v_it & 1;
-                        umma::mbar_wait(&v_empty[vs_i], ((v_it >> 1) & 1) ^ 1);
+                        constexpr int kVS = L::kVStages > 0 ? L::kVStages : 1;
+                        const int vs_i = v_it % kVS;
+                        umma::mbar_wait(&v_empty[vs_i], ((v_it / kVS) & 1) ^ 1);
                         umma::mbar_arrive_expect_tx(&v_full[vs_i], L::kStageBytes);
                         for (int kp = 0; kp < L::kPanels; ++kp)
                             umma::tma_load_4d(s_vstage + vs_i * L::kStageBytes + kp * (kEaTile * 128), &mapV,
@@ -353,8 +360,9 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                 if (kInKernelV && v_active && (t % n_split) == pair) {
                     // kHalves == 1: exactly one warpgroup has no accumulator to drain for this tile — it takes ||v||
                     if ((int)(h_it & 1) != wg) {
-                        const int vs_i = v_it & 1;
-                        umma::mbar_wait(&v_full[vs_i], (v_it >> 1) & 1);
+                        constexpr int kVS = L::kVStages > 0 ? L::kVStages : 1;
+                        const int vs_i = v_it % kVS;
+                        umma::mbar_wait(&v_full[vs_i], (v_it / kVS) & 1);
                         const unsigned char* vrow = s_vstage + vs_i * L::kStageBytes;
                         float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll
@@ -918,7 +926,7 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
 #define KVP_EA_RESIDENT_HEADS 2  // A/B knob: 4 = round-1 layout (all four heads of a Llama-3.1-8B group in one CTA)
 #endif
     const bool tc_path = cov != nullptr && (d.D == 128 || d.D == 64);
-    const bool in_kernel_v = use_vnorm && tc_path && (G <= 2 || KVP_EA_RESIDENT_HEADS == 2);
+    const bool in_kernel_v = KVP_EA_V_STAGES > 0 && use_vnorm && tc_path && (G <= 2 || KVP_EA_RESIDENT_HEADS == 2);
     const void* v_for_logits = in_kernel_v ? V : nullptr;
     EaSideStream* side = (use_vnorm && !in_kernel_v) ? ea_side_stream() : nullptr;
     // host threads enqueueing on different streams of one device share the side stream and its two

@@ -104,16 +104,23 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     {
         const char* k_src = reinterpret_cast<const char*>(K) + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2;
         const char* v_src = reinterpret_cast<const char*>(V) + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2;
-        const int total = n_rows * nvec;
-        for (int i = tid; i < total; i += kClThreads) {
-            const int r = i / nvec, cc = i - r * nvec;
-            cp_async16(&ktile[i], k_src + (int64_t)(start + r) * ks.s * 2 + cc * 16);
-        }
-        if (v_smem)
+        // thread -> (16-byte piece cc, rows r0, r0 + rstep, ...): no integer division per request when D/8 divides 256
+        const bool pow2 = (kClThreads % nvec) == 0;
+        const int cc0 = pow2 ? tid % nvec : 0, r0 = pow2 ? tid / nvec : 0, rstep = pow2 ? kClThreads / nvec : 0;
+        if (pow2) {
+            const char* kp = k_src + (int64_t)start * ks.s * 2 + cc0 * 16;
+            const char* vp = v_src + (int64_t)start * vs.s * 2 + cc0 * 16;
+            for (int r = r0; r < n_rows; r += rstep) cp_async16(&ktile[r * nvec + cc0], kp + (int64_t)r * ks.s * 2);
+            if (v_smem)
+                for (int r = r0; r < n_rows; r += rstep) cp_async16(&vtile[r * nvec + cc0], vp + (int64_t)r * vs.s * 2);
+        } else {
+            const int total = n_rows * nvec;
             for (int i = tid; i < total; i += kClThreads) {
                 const int r = i / nvec, cc = i - r * nvec;
-                cp_async16(&vtile[i], v_src + (int64_t)(start + r) * vs.s * 2 + cc * 16);
+                cp_async16(&ktile[i], k_src + (int64_t)(start + r) * ks.s * 2 + cc * 16);
+                if (v_smem) cp_async16(&vtile[i], v_src + (int64_t)(start + r) * vs.s * 2 + cc * 16);
             }
+        }
     }
     // all CTAs of the cluster have started (their shared memory exists) before anyone writes into it; the barrier
     // overlaps the loads in flight
@@ -131,32 +138,45 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
         constexpr int ROWS_PER_PASS = (kClThreads / 32) * RPW;
         const int sub = lane % LPR, rsel = lane / LPR;
         const int n_pass = (P + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
-#pragma unroll 2
-        for (int j = 0; j < n_pass; ++j) {
-            const int r = j * ROWS_PER_PASS + warp * RPW + rsel;
-            const bool in_slice = r < P;
-            const bool valid = r < n_rows;
-            int4 v = make_int4(0, 0, 0, 0);
-            if (valid && sub < nvec) v = ktile[(size_t)r * nvec + sub];
-            const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
-            float ss = 0.f;
+        constexpr int UI = 4;  // rows in flight per sub-warp: the pass is a chain of LDS -> FMA -> shuffles otherwise
+#pragma unroll 1
+        for (int j0 = 0; j0 < n_pass; j0 += UI) {
+            int4 v[UI];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float2 f = F16Traits<T>::unpack2(w[q]);
-                ss = fmaf(f.x, f.x, ss);
-                ss = fmaf(f.y, f.y, ss);
+            for (int u = 0; u < UI; ++u) {
+                const int r = (j0 + u) * ROWS_PER_PASS + warp * RPW + rsel;
+                v[u] = make_int4(0, 0, 0, 0);
+                if (r < n_rows && sub < nvec) v[u] = ktile[(size_t)r * nvec + sub];
+            }
+            float ss[UI];
+#pragma unroll
+            for (int u = 0; u < UI; ++u) {
+                const uint32_t w[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z, (uint32_t)v[u].w};
+                ss[u] = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = F16Traits<T>::unpack2(w[q]);
+                    ss[u] = fmaf(f.x, f.x, ss[u]);
+                    ss[u] = fmaf(f.y, f.y, ss[u]);
+                }
             }
 #pragma unroll
-            for (int off = LPR / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
-            if (sub == 0 && in_slice) {
-                uint16_t key = 0;
-                if (valid) {
-                    // -sqrt(ss) rounded once to the storage dtype (negation is exact): knorm_press.py:38
-                    const uint16_t bits = F16Traits<T>::from_float(sqrtf(ss)) ^ 0x8000u;
-                    key = ordered_key16(bits, F16Traits<T>::kInfBits);
-                    if (scores_out != nullptr) scores_out[(size_t)row * S + start + r] = bits;
+            for (int off = LPR / 2; off >= 1; off >>= 1)
+#pragma unroll
+                for (int u = 0; u < UI; ++u) ss[u] += __shfl_xor_sync(0xFFFFFFFFu, ss[u], off);
+#pragma unroll
+            for (int u = 0; u < UI; ++u) {
+                const int r = (j0 + u) * ROWS_PER_PASS + warp * RPW + rsel;
+                if (sub == 0 && r < P) {
+                    uint16_t key = 0;
+                    if (r < n_rows) {
+                        // -sqrt(ss) rounded once to the storage dtype (negation is exact): knorm_press.py:38
+                        const uint16_t bits = F16Traits<T>::from_float(sqrtf(ss[u])) ^ 0x8000u;
+                        key = ordered_key16(bits, F16Traits<T>::kInfBits);
+                        if (scores_out != nullptr) scores_out[(size_t)row * S + start + r] = bits;
+                    }
+                    my_keys[r] = key;
                 }
-                my_keys[r] = key;
             }
         }
     }
@@ -219,9 +239,15 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
         uint32_t c = 0;
 #pragma unroll
         for (int i = 0; i < kClMaxKeysPerThread; ++i) c += myk[i] >= cand;
-        uint32_t tot[3];
-        block_sum3(c, 0u, 0u, bit & 1, tot);  // alternating slots: one barrier per step is enough
-        if (tot[0] >= (uint32_t)n_kept) T1 = cand;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, off);
+        const int slot = bit & 1;  // alternating slots: one barrier per step is enough
+        if (lane == 0) red3[slot][0][warp] = c;
+        __syncthreads();
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) total += red3[slot][0][w];
+        if (total >= (uint32_t)n_kept) T1 = cand;
     }
     // kept (> T) positions of the row, and kept / tied positions in front of this CTA's slice
     uint32_t n_gt = 0, gt_b = 0, eq_b = 0;
@@ -287,11 +313,21 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     const uint64_t pol_first = l2_policy_evict_first();
     const int total = (int)count * nvec;
     if (v_smem) {  // both tensors come from shared memory: pure stores
-        for (int i = tid; i < total; i += kClThreads) {
-            const int r = i / nvec, cc = i - r * nvec;
-            const int64_t off = (int64_t)r * row_bytes + cc * 16;
-            stg_hint(k_dst + off, ktile[(size_t)list[r] * nvec + cc], pol_first);
-            stg_hint(v_dst + off, vtile[(size_t)list[r] * nvec + cc], pol_first);
+        if ((kClThreads % nvec) == 0) {
+            const int cc = tid % nvec, rstep = kClThreads / nvec;
+            for (int r = tid / nvec; r < (int)count; r += rstep) {
+                const int64_t off = (int64_t)r * row_bytes + cc * 16;
+                const int src = list[r] * nvec + cc;
+                stg_hint(k_dst + off, ktile[src], pol_first);
+                stg_hint(v_dst + off, vtile[src], pol_first);
+            }
+        } else {
+            for (int i = tid; i < total; i += kClThreads) {
+                const int r = i / nvec, cc = i - r * nvec;
+                const int64_t off = (int64_t)r * row_bytes + cc * 16;
+                stg_hint(k_dst + off, ktile[(size_t)list[r] * nvec + cc], pol_first);
+                stg_hint(v_dst + off, vtile[(size_t)list[r] * nvec + cc], pol_first);
+            }
         }
         CL_MARK(9);
         return;
