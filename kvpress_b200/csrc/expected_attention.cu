@@ -485,7 +485,15 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     }
                 }
                 __syncwarp();
-                if (!released_k && lane == 0) umma::mbar_arrive(&k_empty[stage]);  // skipped this K tile
+                if (!released_k) {
+                    // This warpgroup had nothing to drain for tile t, but it still owes the stage its release. It must
+                    // not give it before the tile has LANDED: an early arrival would be counted in the phase of the
+                    // stage's PREVIOUS tile (whose other consumers may still be reading it) and complete that phase
+                    // too soon — the producer would then overwrite a tile in use. Seen as a sporadic launch failure
+                    // once the idle warpgroup got other work (value norms) and tiles got short (G = 1).
+                    umma::mbar_wait(&k_full[stage], (k_it / kStages) & 1);
+                    if (lane == 0) umma::mbar_arrive(&k_empty[stage]);
+                }
             }
             // ---- warp-level (max, sum-exp) per head slot -> shared ---------------------------------------
 #pragma unroll

@@ -4,21 +4,23 @@
 //
 // At these sizes (tens of MB) the call is latency-bound: the multi-kernel path spends its time in launch gaps, a
 // memset node, global atomics and spin-waits between CTAs. Here one thread-block CLUSTER owns one (b, h) row:
-//   1. every CTA requests its whole slice of the row with cp.async up front — every K row, and every V row when both
-//      fit — so the slice is one memory round trip, then scores it from shared memory (fp32 sum of squares, one
-//      rounding);
+//   1. every CTA requests its whole slice of the row up front as one bulk copy (cp.async.bulk, the TMA engine) per row —
+//      every K row, and every V row when both fit — completing on one mbarrier: the slice is one memory round trip and
+//      a few hundred instructions; then one thread per row scores it from shared memory (fp32 sum of squares, one
+//      rounding; rows sit at a pitch of 2*D + 16 bytes so that the per-thread row reads are bank-conflict free);
 //   2. the 16-bit ordered keys of the slice are pushed into the shared memory of every CTA of the cluster
 //      (distributed shared memory), ONE cluster barrier;
 //   3. every CTA now holds the keys of the whole row and derives the exact threshold, the tie budget and the number
-//      of kept positions in front of its slice on its own (a 17-step search over the threshold's bits: register-only
-//      counts + block reductions, no atomics);
-//   4. it ranks its slice and writes the kept K (and V) rows from shared memory — V from global memory when it was
-//      not staged — to their final places (ascending positions, ties to the lowest positions — same rule as select_compact.cu).
+//      of kept positions in front of its slice on its own (a search over the threshold's bits, two per step:
+//      register-only counts, redux.sync warp sums, one barrier per step — no atomics);
+//   4. it ranks its slice and writes the kept K (and V) rows from shared memory with one bulk store per row — V through
+//      registers from global memory when it was not staged — to their final places (ascending positions, ties to the lowest positions — same rule as select_compact.cu).
 // No global atomics, no flags, no workspace: the only inter-CTA communication is the key exchange.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -52,11 +54,13 @@ struct ClusterPlan {
     bool ok;
 };
 
+__host__ __device__ constexpr int cl_pitch(int D) { return D * 2 + 16; }  // bytes between staged rows
+
 static ClusterPlan cluster_plan(const Dims& d, int C) {
     ClusterPlan pl;
     pl.C = C;
     pl.P = ((d.S + C - 1) / C + 7) / 8 * 8;
-    const size_t tile = (size_t)pl.P * d.D * 2;
+    const size_t tile = (size_t)pl.P * cl_pitch(d.D);
     const size_t keys = (size_t)C * pl.P * 2;
     const size_t list = (size_t)pl.P * 4;
     pl.v_smem = (2 * tile + keys + list + 64 <= (size_t)kClMaxSmem) ? 1 : 0;
@@ -65,16 +69,24 @@ static ClusterPlan cluster_plan(const Dims& d, int C) {
     return pl;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gmem_src)
+// one row: global -> shared through the bulk-copy engine, completion counted on `bar`
+__device__ __forceinline__ void bulk_load_row(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     umma::smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(umma::smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+// one row: shared -> global
+__device__ __forceinline__ void bulk_store_row(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(umma::smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_wait() {
+    asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-template <typename T, int LPR>
+template <typename T>
 __global__ void __launch_bounds__(kClThreads, 1)
 knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks, Strides3 vs,
                      char* __restrict__ K_out, char* __restrict__ V_out, int32_t* __restrict__ idx_out,
@@ -86,40 +98,36 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     const int row = blockIdx.y, b = row / H, h = row % H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nvec = D >> 3;
+    const int pitch = cl_pitch(D);
+    const uint32_t row_bytes = (uint32_t)D * 2;
 
-    const size_t tile_bytes = (size_t)P * D * 2;
-    int4* ktile = reinterpret_cast<int4*>(smem);                                         // [P][nvec] 16-byte pieces
-    int4* vtile = reinterpret_cast<int4*>(smem + tile_bytes);                            // [P][nvec], only if v_smem
+    const size_t tile_bytes = (size_t)P * pitch;
+    unsigned char* ktile = smem;                     // [P] rows at `pitch`
+    unsigned char* vtile = smem + tile_bytes;        // [P] rows, only if v_smem
     unsigned char* after = smem + (v_smem ? 2 : 1) * tile_bytes;
     uint16_t* all_keys = reinterpret_cast<uint16_t*>(after);                             // [C][P]
     int* list = reinterpret_cast<int*>(after + (size_t)C * P * 2);                       // [P] kept local positions
     __shared__ uint32_t red[2][8];
     __shared__ uint32_t red3[2][3][8];
+    __shared__ __align__(8) uint64_t load_bar;
 
-    // ---- 1. stage the slice [start, start + P): every K row (and every V row when it fits) is requested up front
-    // with cp.async, so the whole slice is ONE memory round trip and costs no registers -----------------------------
+    // ---- 1. stage the slice [start, start + P): one bulk copy per row, all in flight at once --------------------------
     const int start = rank * P;
     const int n_rows = max(0, min(P, S - start));
     CL_MARK(0);
+    if (tid == 0) {
+        umma::mbar_init(&load_bar, 1);
+        umma::mbar_fence_init();
+    }
+    __syncthreads();
     {
         const char* k_src = reinterpret_cast<const char*>(K) + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2;
         const char* v_src = reinterpret_cast<const char*>(V) + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2;
-        // thread -> (16-byte piece cc, rows r0, r0 + rstep, ...): no integer division per request when D/8 divides 256
-        const bool pow2 = (kClThreads % nvec) == 0;
-        const int cc0 = pow2 ? tid % nvec : 0, r0 = pow2 ? tid / nvec : 0, rstep = pow2 ? kClThreads / nvec : 0;
-        if (pow2) {
-            const char* kp = k_src + (int64_t)start * ks.s * 2 + cc0 * 16;
-            const char* vp = v_src + (int64_t)start * vs.s * 2 + cc0 * 16;
-            for (int r = r0; r < n_rows; r += rstep) cp_async16(&ktile[r * nvec + cc0], kp + (int64_t)r * ks.s * 2);
+        if (tid == 0) umma::mbar_arrive_expect_tx(&load_bar, (uint32_t)n_rows * row_bytes * (v_smem ? 2u : 1u));
+        for (int r = tid; r < n_rows; r += kClThreads) {
+            bulk_load_row(ktile + (size_t)r * pitch, k_src + (int64_t)(start + r) * ks.s * 2, row_bytes, &load_bar);
             if (v_smem)
-                for (int r = r0; r < n_rows; r += rstep) cp_async16(&vtile[r * nvec + cc0], vp + (int64_t)r * vs.s * 2);
-        } else {
-            const int total = n_rows * nvec;
-            for (int i = tid; i < total; i += kClThreads) {
-                const int r = i / nvec, cc = i - r * nvec;
-                cp_async16(&ktile[i], k_src + (int64_t)(start + r) * ks.s * 2 + cc * 16);
-                if (v_smem) cp_async16(&vtile[i], v_src + (int64_t)(start + r) * vs.s * 2 + cc * 16);
-            }
+                bulk_load_row(vtile + (size_t)r * pitch, v_src + (int64_t)(start + r) * vs.s * 2, row_bytes, &load_bar);
         }
     }
     // all CTAs of the cluster have started (their shared memory exists) before anyone writes into it; the barrier
@@ -127,58 +135,31 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     CL_MARK(1);
     cluster.sync();
     CL_MARK(2);
-    cp_async_wait_all();
-    __syncthreads();
+    umma::mbar_wait(&load_bar, 0);
     CL_MARK(3);
 
-    // ---- score the slice from shared memory --------------------------------------------------------------------------
+    // ---- score the slice from shared memory: one thread per row, fixed summation order ----------------------------------
     uint16_t* my_keys = all_keys + (size_t)rank * P;
-    {
-        constexpr int RPW = 32 / LPR;
-        constexpr int ROWS_PER_PASS = (kClThreads / 32) * RPW;
-        const int sub = lane % LPR, rsel = lane / LPR;
-        const int n_pass = (P + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
-        constexpr int UI = 4;  // rows in flight per sub-warp: the pass is a chain of LDS -> FMA -> shuffles otherwise
-#pragma unroll 1
-        for (int j0 = 0; j0 < n_pass; j0 += UI) {
-            int4 v[UI];
-#pragma unroll
-            for (int u = 0; u < UI; ++u) {
-                const int r = (j0 + u) * ROWS_PER_PASS + warp * RPW + rsel;
-                v[u] = make_int4(0, 0, 0, 0);
-                if (r < n_rows && sub < nvec) v[u] = ktile[(size_t)r * nvec + sub];
+    for (int r = tid; r < P; r += kClThreads) {
+        uint16_t key = 0;
+        if (r < n_rows) {
+            const int4* rp = reinterpret_cast<const int4*>(ktile + (size_t)r * pitch);
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            for (int c = 0; c < nvec; ++c) {
+                const int4 v = rp[c];
+                const float2 f0 = F16Traits<T>::unpack2((uint32_t)v.x), f1 = F16Traits<T>::unpack2((uint32_t)v.y);
+                const float2 f2 = F16Traits<T>::unpack2((uint32_t)v.z), f3 = F16Traits<T>::unpack2((uint32_t)v.w);
+                s0 = fmaf(f0.x, f0.x, s0); s1 = fmaf(f0.y, f0.y, s1);
+                s2 = fmaf(f1.x, f1.x, s2); s3 = fmaf(f1.y, f1.y, s3);
+                s0 = fmaf(f2.x, f2.x, s0); s1 = fmaf(f2.y, f2.y, s1);
+                s2 = fmaf(f3.x, f3.x, s2); s3 = fmaf(f3.y, f3.y, s3);
             }
-            float ss[UI];
-#pragma unroll
-            for (int u = 0; u < UI; ++u) {
-                const uint32_t w[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z, (uint32_t)v[u].w};
-                ss[u] = 0.f;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 f = F16Traits<T>::unpack2(w[q]);
-                    ss[u] = fmaf(f.x, f.x, ss[u]);
-                    ss[u] = fmaf(f.y, f.y, ss[u]);
-                }
-            }
-#pragma unroll
-            for (int off = LPR / 2; off >= 1; off >>= 1)
-#pragma unroll
-                for (int u = 0; u < UI; ++u) ss[u] += __shfl_xor_sync(0xFFFFFFFFu, ss[u], off);
-#pragma unroll
-            for (int u = 0; u < UI; ++u) {
-                const int r = (j0 + u) * ROWS_PER_PASS + warp * RPW + rsel;
-                if (sub == 0 && r < P) {
-                    uint16_t key = 0;
-                    if (r < n_rows) {
-                        // -sqrt(ss) rounded once to the storage dtype (negation is exact): knorm_press.py:38
-                        const uint16_t bits = F16Traits<T>::from_float(sqrtf(ss[u])) ^ 0x8000u;
-                        key = ordered_key16(bits, F16Traits<T>::kInfBits);
-                        if (scores_out != nullptr) scores_out[(size_t)row * S + start + r] = bits;
-                    }
-                    my_keys[r] = key;
-                }
-            }
+            // -sqrt(ss) rounded once to the storage dtype (negation is exact): knorm_press.py:38
+            const uint16_t bits = F16Traits<T>::from_float(sqrtf((s0 + s1) + (s2 + s3))) ^ 0x8000u;
+            key = ordered_key16(bits, F16Traits<T>::kInfBits);
+            if (scores_out != nullptr) scores_out[(size_t)row * S + start + r] = bits;
         }
+        my_keys[r] = key;
     }
     __syncthreads();
     CL_MARK(4);
@@ -200,10 +181,9 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     // ---- 3. exact threshold of the row, computed redundantly by every CTA -----------------------------------------
     // The whole row's keys sit in shared memory (position s at all_keys[s]: slices are contiguous); every thread takes
     // the positions tid, tid + 256, ... into registers. The threshold T = the n_kept-th largest key is found by a
-    // 16-step search over its bits — T |= bit whenever at least n_kept keys are >= T | bit — each step one
-    // register-only count + one block reduction. No shared-memory atomics: Knorm scores of a row take ~100 distinct
-    // values, so histogram bins would be hammered by every warp at once (the first version of this kernel spent most
-    // of its time there).
+    // search over its bits, two per step: T |= the largest 2-bit digit d with count(key >= T | d << shift) >= n_kept.
+    // No shared-memory atomics: Knorm scores of a row take ~100 distinct values, histogram bins would be hammered by
+    // every warp at once.
     uint32_t myk[kClMaxKeysPerThread];
     const int n_mine = (S + kClThreads - 1) / kClThreads;  // <= kClMaxKeysPerThread (cluster_plan)
 #pragma unroll
@@ -211,13 +191,11 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
         const int s = i * kClThreads + tid;
         myk[i] = (i < n_mine && s < S) ? (uint32_t)all_keys[s] + 1u : 0u;  // +1: 0 marks "no position", below any key
     }
+    // block-wide sums of three counters: redux.sync per warp, one barrier; `slot` alternates between calls
     auto block_sum3 = [&](uint32_t a, uint32_t b2, uint32_t c, int slot, uint32_t (&out)[3]) {
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            a += __shfl_xor_sync(0xFFFFFFFFu, a, off);
-            b2 += __shfl_xor_sync(0xFFFFFFFFu, b2, off);
-            c += __shfl_xor_sync(0xFFFFFFFFu, c, off);
-        }
+        a = __reduce_add_sync(0xFFFFFFFFu, a);
+        b2 = __reduce_add_sync(0xFFFFFFFFu, b2);
+        c = __reduce_add_sync(0xFFFFFFFFu, c);
         if (lane == 0) {
             red3[slot][0][warp] = a;
             red3[slot][1][warp] = b2;
@@ -232,22 +210,25 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
             out[2] += red3[slot][2][w];
         }
     };
-    uint32_t T1 = 0;  // threshold in the shifted (+1) key space
+    uint32_t T1 = 0;  // threshold in the shifted (+1) key space: 17 bits = bit 16 alone, then 8 two-bit digits
+    int it = 0;
 #pragma unroll 1
-    for (int bit = 16; bit >= 0; --bit) {  // shifted keys span 17 bits
-        const uint32_t cand = T1 | (1u << bit);
-        uint32_t c = 0;
+    for (int shift = 16; shift >= 0; shift -= 2, ++it) {
+        const uint32_t c1 = T1 | (1u << shift), c2 = T1 | (2u << shift), c3 = T1 | (3u << shift);
+        const bool single = shift == 16;  // digits 2 and 3 would be bits 17, 18: no key reaches them
+        uint32_t n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
-        for (int i = 0; i < kClMaxKeysPerThread; ++i) c += myk[i] >= cand;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, off);
-        const int slot = bit & 1;  // alternating slots: one barrier per step is enough
-        if (lane == 0) red3[slot][0][warp] = c;
-        __syncthreads();
-        uint32_t total = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) total += red3[slot][0][w];
-        if (total >= (uint32_t)n_kept) T1 = cand;
+        for (int i = 0; i < kClMaxKeysPerThread; ++i) {
+            n1 += myk[i] >= c1;
+            n2 += myk[i] >= c2;
+            n3 += myk[i] >= c3;
+        }
+        uint32_t tot[3];
+        block_sum3(n1, single ? 0u : n2, single ? 0u : n3, it & 1, tot);
+        const uint32_t need = (uint32_t)n_kept;
+        if (!single && tot[2] >= need) T1 = c3;
+        else if (!single && tot[1] >= need) T1 = c2;
+        else if (tot[0] >= need) T1 = c1;
     }
     // kept (> T) positions of the row, and kept / tied positions in front of this CTA's slice
     uint32_t n_gt = 0, gt_b = 0, eq_b = 0;
@@ -259,8 +240,7 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
         eq_b += front && myk[i] == T1;
     }
     uint32_t tot[3];
-    __syncthreads();  // slot 0 was last read in the bit loop
-    block_sum3(n_gt, gt_b, eq_b, 0, tot);
+    block_sum3(n_gt, gt_b, eq_b, it & 1, tot);
     const uint32_t T16 = T1 - 1u;                       // back to the 16-bit key space (T1 >= 1: n_kept >= 1)
     const uint32_t n_take = (uint32_t)n_kept - tot[0];  // ties (key == T) to take, lowest positions first
     const uint32_t gt_before = tot[1], eq_before = tot[2];
@@ -273,7 +253,7 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     uint32_t count = 0;                          // kept rows of this slice so far
     for (int c0 = 0; c0 < P; c0 += kClThreads) {
         const int r = c0 + tid;
-        const bool valid = r < P && start + r < S;
+        const bool valid = r < n_rows;
         const uint32_t key = valid ? my_keys[r] : 0u;
         const bool is_gt = valid && key > T16;
         const bool is_eq = valid && key == T16;
@@ -306,61 +286,47 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     const int64_t out_row0 = (int64_t)row * n_kept + out_base;
     if (idx_out != nullptr)
         for (uint32_t i = tid; i < count; i += kClThreads) idx_out[out_row0 + i] = start + list[i];
-    const int64_t row_bytes = (int64_t)D * 2;
-    const char* v_src = reinterpret_cast<const char*>(V) + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2;
-    char* k_dst = K_out + out_row0 * row_bytes;
-    char* v_dst = V_out + out_row0 * row_bytes;
-    const uint64_t pol_first = l2_policy_evict_first();
-    const int total = (int)count * nvec;
-    if (v_smem) {  // both tensors come from shared memory: pure stores
-        if ((kClThreads % nvec) == 0) {
-            const int cc = tid % nvec, rstep = kClThreads / nvec;
-            for (int r = tid / nvec; r < (int)count; r += rstep) {
-                const int64_t off = (int64_t)r * row_bytes + cc * 16;
-                const int src = list[r] * nvec + cc;
-                stg_hint(k_dst + off, ktile[src], pol_first);
-                stg_hint(v_dst + off, vtile[src], pol_first);
-            }
-        } else {
-            for (int i = tid; i < total; i += kClThreads) {
-                const int r = i / nvec, cc = i - r * nvec;
-                const int64_t off = (int64_t)r * row_bytes + cc * 16;
-                stg_hint(k_dst + off, ktile[(size_t)list[r] * nvec + cc], pol_first);
-                stg_hint(v_dst + off, vtile[(size_t)list[r] * nvec + cc], pol_first);
-            }
-        }
-        CL_MARK(9);
-        return;
+    char* k_dst = K_out + out_row0 * (int64_t)row_bytes;
+    char* v_dst = V_out + out_row0 * (int64_t)row_bytes;
+    // kept rows leave shared memory with one bulk store each (the tiles were written by the same async proxy)
+    for (uint32_t r = tid; r < count; r += kClThreads) {
+        bulk_store_row(k_dst + (int64_t)r * row_bytes, ktile + (size_t)list[r] * pitch, row_bytes);
+        if (v_smem) bulk_store_row(v_dst + (int64_t)r * row_bytes, vtile + (size_t)list[r] * pitch, row_bytes);
     }
-    constexpr int UC = 8;
-    for (int base = tid; base < total; base += kClThreads * UC) {
-        int4 vv[UC];
+    if (!v_smem) {  // V was not staged: kept rows through registers
+        const char* v_src = reinterpret_cast<const char*>(V) + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2;
+        const uint64_t pol_first = l2_policy_evict_first();
+        const int total = (int)count * nvec;
+        constexpr int UC = 8;
+        for (int base = tid; base < total; base += kClThreads * UC) {
+            int4 vv[UC];
 #pragma unroll
-        for (int u = 0; u < UC; ++u) {
-            const int i = base + u * kClThreads;
-            if (i < total) {
-                const int r = i / nvec, cc = i - r * nvec;
-                vv[u] = ldg_hint(v_src + (int64_t)(start + list[r]) * vs.s * 2 + cc * 16, pol_first);
+            for (int u = 0; u < UC; ++u) {
+                const int i = base + u * kClThreads;
+                if (i < total) {
+                    const int r = i / nvec, cc = i - r * nvec;
+                    vv[u] = ldg_hint(v_src + (int64_t)(start + list[r]) * vs.s * 2 + cc * 16, pol_first);
+                }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < UC; ++u) {
-            const int i = base + u * kClThreads;
-            if (i < total) {
-                const int r = i / nvec, cc = i - r * nvec;
-                const int64_t off = (int64_t)r * row_bytes + cc * 16;
-                stg_hint(k_dst + off, ktile[(size_t)list[r] * nvec + cc], pol_first);
-                stg_hint(v_dst + off, vv[u], pol_first);
+            for (int u = 0; u < UC; ++u) {
+                const int i = base + u * kClThreads;
+                if (i < total) {
+                    const int r = i / nvec, cc = i - r * nvec;
+                    stg_hint(v_dst + (int64_t)r * row_bytes + cc * 16, vv[u], pol_first);
+                }
             }
         }
     }
+    bulk_store_wait();  // shared memory must stay valid until the bulk stores have read it
+    CL_MARK(9);
 }
 
-template <typename T, int LPR>
+template <typename T>
 static cudaError_t launch_cluster_t(const Dims& d, const ClusterPlan& pl, const void* K, const void* V, void* K_out,
                                     void* V_out, int32_t* idx_out, void* scores_out, cudaStream_t st) {
-    auto kern = knorm_cluster_kernel<T, LPR>;
-    static PerDeviceOnce smem_set;  // one per <T, LPR> instantiation of this launcher
+    auto kern = knorm_cluster_kernel<T>;
+    static PerDeviceOnce smem_set;  // one per <T> instantiation of this launcher
     cudaError_t e = ensure_dynamic_smem(kern, kClMaxSmem, smem_set);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -404,16 +370,8 @@ cudaError_t launch_knorm_cluster(const Dims& d, int dtype, const void* K, const 
                                  int32_t* idx_out, void* scores_out, cudaStream_t st) {
     ClusterPlan pl;
     if (!choose_cluster(d, &pl)) return cudaErrorNotSupported;
-    const int nvec = d.D / 8;
-#define KVP_CL(LPR)                                                                                             \
-    return (dtype == KVP_BF16)                                                                                   \
-               ? launch_cluster_t<__nv_bfloat16, LPR>(d, pl, K, V, K_out, V_out, idx_out, scores_out, st)       \
-               : launch_cluster_t<__half, LPR>(d, pl, K, V, K_out, V_out, idx_out, scores_out, st)
-    if (nvec <= 4) KVP_CL(4);
-    if (nvec <= 8) KVP_CL(8);
-    if (nvec <= 16) KVP_CL(16);
-    KVP_CL(32);
-#undef KVP_CL
+    return (dtype == KVP_BF16) ? launch_cluster_t<__nv_bfloat16>(d, pl, K, V, K_out, V_out, idx_out, scores_out, st)
+                               : launch_cluster_t<__half>(d, pl, K, V, K_out, V_out, idx_out, scores_out, st);
 }
 
 }  // namespace kvp

@@ -641,7 +641,7 @@ knorm_fused_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks
         if (it.kind == 0) {
             sm.hist[tid] = 0;
             if (k_evict_last)
-                knorm_score_chunk<T, LPR, true>(K, ks, it.row / H, it.row % H, it.idx, S, D, skeys, sscores);
+                knorm_score_chunk<T, LPR, 1>(K, ks, it.row / H, it.row % H, it.idx, S, D, skeys, sscores);
             else
                 knorm_score_chunk<T, LPR>(K, ks, it.row / H, it.row % H, it.idx, S, D, skeys, sscores);
             __syncthreads();
