@@ -268,16 +268,21 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                     for (int kp = 0; kp < L::kPanels; ++kp)
                         umma::tma_load_4d(s_stage + stage * L::kStageBytes + kp * (kEaTile * 128),
                                           &mapK, &k_full[stage], kp * 64, t * kEaTile, h, b);
-                    if (v_active && (t % n_split) == pair) {
-                        constexpr int kVS = L::kVStages > 0 ? L::kVStages : 1;
-                        const int vs_i = v_it % kVS;
-                        umma::mbar_wait(&v_empty[vs_i], ((v_it / kVS) & 1) ^ 1);
-                        umma::mbar_arrive_expect_tx(&v_full[vs_i], L::kStageBytes);
-                        for (int kp = 0; kp < L::kPanels; ++kp)
-                            umma::tma_load_4d(s_vstage + vs_i * L::kStageBytes + kp * (kEaTile * 128), &mapV,
-                                              &v_full[vs_i], kp * 64, t * kEaTile, h, b);
-                        ++v_it;
-                    }
+                }
+            }
+        } else if (warp == 3) {
+            // ===== V producer (own thread: a full V ring must never hold back the K prefetch) =====
+            if (lane == 0 && v_active) {
+                constexpr int kVS = L::kVStages > 0 ? L::kVStages : 1;
+                for (int t = t_begin; t < t_end; ++t) {
+                    if ((t % n_split) != pair) continue;
+                    const int vs_i = v_it % kVS;
+                    umma::mbar_wait(&v_empty[vs_i], ((v_it / kVS) & 1) ^ 1);
+                    umma::mbar_arrive_expect_tx(&v_full[vs_i], L::kStageBytes);
+                    for (int kp = 0; kp < L::kPanels; ++kp)
+                        umma::tma_load_4d(s_vstage + vs_i * L::kStageBytes + kp * (kEaTile * 128), &mapV,
+                                          &v_full[vs_i], kp * 64, t * kEaTile, h, b);
+                    ++v_it;
                 }
             }
         } else if (warp == 1) {
@@ -358,11 +363,14 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                 const bool valid = (s >= n_sink) && (s < S);
                 bool waited_k = false, released_k = false;
                 if (kInKernelV && v_active && (t % n_split) == pair) {
-                    // kHalves == 1: exactly one warpgroup has no accumulator to drain for this tile — it takes ||v||
+                    // kHalves == 1: exactly one warpgroup has no accumulator to drain for this tile — it takes ||v||.
+                    // BOTH warpgroups wait for the V tile: a waiter that skipped a phase of v_full would test the
+                    // wrong parity the next time it is the reader (with one V stage and n_split odd the reader
+                    // alternates) and read a tile that has not landed.
+                    constexpr int kVS = L::kVStages > 0 ? L::kVStages : 1;
+                    const int vs_i = v_it % kVS;
+                    umma::mbar_wait(&v_full[vs_i], (v_it / kVS) & 1);
                     if ((int)(h_it & 1) != wg) {
-                        constexpr int kVS = L::kVStages > 0 ? L::kVStages : 1;
-                        const int vs_i = v_it % kVS;
-                        umma::mbar_wait(&v_full[vs_i], (v_it / kVS) & 1);
                         const unsigned char* vrow = s_vstage + vs_i * L::kStageBytes;
                         float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll

@@ -54,7 +54,8 @@ struct ClusterPlan {
     bool ok;
 };
 
-__host__ __device__ constexpr int cl_pitch(int D) { return D * 2 + 16; }  // bytes between staged rows
+__host__ __device__ constexpr int cl_pitch(int D) { return D * 2; }  // bytes between staged rows (dense: runs of rows
+                                                                      // move as one bulk copy)
 
 static ClusterPlan cluster_plan(const Dims& d, int C) {
     ClusterPlan pl;
@@ -86,7 +87,7 @@ __device__ __forceinline__ void bulk_store_wait() {
     asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-template <typename T>
+template <typename T, int KPT>  // KPT: keys of the row per thread held in registers (S <= 256 * KPT)
 __global__ void __launch_bounds__(kClThreads, 1)
 knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 ks, Strides3 vs,
                      char* __restrict__ K_out, char* __restrict__ V_out, int32_t* __restrict__ idx_out,
@@ -124,10 +125,30 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
         const char* k_src = reinterpret_cast<const char*>(K) + ((int64_t)b * ks.b + (int64_t)h * ks.h) * 2;
         const char* v_src = reinterpret_cast<const char*>(V) + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2;
         if (tid == 0) umma::mbar_arrive_expect_tx(&load_bar, (uint32_t)n_rows * row_bytes * (v_smem ? 2u : 1u));
-        for (int r = tid; r < n_rows; r += kClThreads) {
-            bulk_load_row(ktile + (size_t)r * pitch, k_src + (int64_t)(start + r) * ks.s * 2, row_bytes, &load_bar);
-            if (v_smem)
-                bulk_load_row(vtile + (size_t)r * pitch, v_src + (int64_t)(start + r) * vs.s * 2, row_bytes, &load_bar);
+        // rows that are dense in global memory (the usual cache layout) move as 16 KB bulk copies, a handful per CTA;
+        // strided views fall back to one bulk copy per row (the copy engine then spends ~5 ns per row)
+        constexpr int kChunk = 16384;
+        const uint32_t slice_bytes = (uint32_t)n_rows * row_bytes;
+        const int n_chunks = (int)((slice_bytes + kChunk - 1) / kChunk);
+        if (ks.s == D) {
+            for (int c = tid; c < n_chunks; c += kClThreads) {
+                const uint32_t off = (uint32_t)c * kChunk, len = min((uint32_t)kChunk, slice_bytes - off);
+                bulk_load_row(ktile + off, k_src + (int64_t)start * row_bytes + off, len, &load_bar);
+            }
+        } else {
+            for (int r = tid; r < n_rows; r += kClThreads)
+                bulk_load_row(ktile + (size_t)r * pitch, k_src + (int64_t)(start + r) * ks.s * 2, row_bytes, &load_bar);
+        }
+        if (v_smem) {
+            if (vs.s == D) {
+                for (int c = kClThreads - 1 - tid; c < n_chunks; c += kClThreads) {  // other threads than the K chunks
+                    const uint32_t off = (uint32_t)c * kChunk, len = min((uint32_t)kChunk, slice_bytes - off);
+                    bulk_load_row(vtile + off, v_src + (int64_t)start * row_bytes + off, len, &load_bar);
+                }
+            } else {
+                for (int r = tid; r < n_rows; r += kClThreads)
+                    bulk_load_row(vtile + (size_t)r * pitch, v_src + (int64_t)(start + r) * vs.s * 2, row_bytes, &load_bar);
+            }
         }
     }
     // all CTAs of the cluster have started (their shared memory exists) before anyone writes into it; the barrier
@@ -143,10 +164,15 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     for (int r = tid; r < P; r += kClThreads) {
         uint16_t key = 0;
         if (r < n_rows) {
+            // rows are dense (pitch = 2 D): a thread starts at piece r % nvec so that the 8 lanes of a quarter warp hit
+            // 8 different bank groups; the order in which a row's pieces are summed therefore depends on the row's
+            // place in the slice — a last-bit effect in fp32, far below the one rounding to the 16-bit score
             const int4* rp = reinterpret_cast<const int4*>(ktile + (size_t)r * pitch);
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            for (int c = 0; c < nvec; ++c) {
+            int c = r % nvec;
+            for (int j = 0; j < nvec; ++j) {
                 const int4 v = rp[c];
+                c = (c + 1 == nvec) ? 0 : c + 1;
                 const float2 f0 = F16Traits<T>::unpack2((uint32_t)v.x), f1 = F16Traits<T>::unpack2((uint32_t)v.y);
                 const float2 f2 = F16Traits<T>::unpack2((uint32_t)v.z), f3 = F16Traits<T>::unpack2((uint32_t)v.w);
                 s0 = fmaf(f0.x, f0.x, s0); s1 = fmaf(f0.y, f0.y, s1);
@@ -184,10 +210,10 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     // search over its bits, two per step: T |= the largest 2-bit digit d with count(key >= T | d << shift) >= n_kept.
     // No shared-memory atomics: Knorm scores of a row take ~100 distinct values, histogram bins would be hammered by
     // every warp at once.
-    uint32_t myk[kClMaxKeysPerThread];
-    const int n_mine = (S + kClThreads - 1) / kClThreads;  // <= kClMaxKeysPerThread (cluster_plan)
+    uint32_t myk[KPT];
+    const int n_mine = (S + kClThreads - 1) / kClThreads;  // <= KPT (launcher)
 #pragma unroll
-    for (int i = 0; i < kClMaxKeysPerThread; ++i) {
+    for (int i = 0; i < KPT; ++i) {
         const int s = i * kClThreads + tid;
         myk[i] = (i < n_mine && s < S) ? (uint32_t)all_keys[s] + 1u : 0u;  // +1: 0 marks "no position", below any key
     }
@@ -218,7 +244,7 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
         const bool single = shift == 16;  // digits 2 and 3 would be bits 17, 18: no key reaches them
         uint32_t n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
-        for (int i = 0; i < kClMaxKeysPerThread; ++i) {
+        for (int i = 0; i < KPT; ++i) {
             n1 += myk[i] >= c1;
             n2 += myk[i] >= c2;
             n3 += myk[i] >= c3;
@@ -233,7 +259,7 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     // kept (> T) positions of the row, and kept / tied positions in front of this CTA's slice
     uint32_t n_gt = 0, gt_b = 0, eq_b = 0;
 #pragma unroll
-    for (int i = 0; i < kClMaxKeysPerThread; ++i) {
+    for (int i = 0; i < KPT; ++i) {
         const bool front = (i * kClThreads + tid) < start;
         n_gt += myk[i] > T1;
         gt_b += front && myk[i] > T1;
@@ -288,10 +314,15 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
         for (uint32_t i = tid; i < count; i += kClThreads) idx_out[out_row0 + i] = start + list[i];
     char* k_dst = K_out + out_row0 * (int64_t)row_bytes;
     char* v_dst = V_out + out_row0 * (int64_t)row_bytes;
-    // kept rows leave shared memory with one bulk store each (the tiles were written by the same async proxy)
+    // kept rows leave shared memory as bulk stores, one per RUN of consecutive kept positions (the tiles are dense and
+    // were written by the same async proxy): at 80 % density that is ~5 rows per store
     for (uint32_t r = tid; r < count; r += kClThreads) {
-        bulk_store_row(k_dst + (int64_t)r * row_bytes, ktile + (size_t)list[r] * pitch, row_bytes);
-        if (v_smem) bulk_store_row(v_dst + (int64_t)r * row_bytes, vtile + (size_t)list[r] * pitch, row_bytes);
+        const int pos = list[r];
+        if (r > 0 && list[r - 1] == pos - 1) continue;  // not the head of a run
+        uint32_t len = 1;
+        while (r + len < count && list[r + len] == pos + (int)len) ++len;
+        bulk_store_row(k_dst + (int64_t)r * row_bytes, ktile + (size_t)pos * pitch, len * row_bytes);
+        if (v_smem) bulk_store_row(v_dst + (int64_t)r * row_bytes, vtile + (size_t)pos * pitch, len * row_bytes);
     }
     if (!v_smem) {  // V was not staged: kept rows through registers
         const char* v_src = reinterpret_cast<const char*>(V) + ((int64_t)b * vs.b + (int64_t)h * vs.h) * 2;
@@ -322,11 +353,11 @@ knorm_cluster_kernel(const T* __restrict__ K, const T* __restrict__ V, Strides3 
     CL_MARK(9);
 }
 
-template <typename T>
+template <typename T, int KPT>
 static cudaError_t launch_cluster_t(const Dims& d, const ClusterPlan& pl, const void* K, const void* V, void* K_out,
                                     void* V_out, int32_t* idx_out, void* scores_out, cudaStream_t st) {
-    auto kern = knorm_cluster_kernel<T>;
-    static PerDeviceOnce smem_set;  // one per <T> instantiation of this launcher
+    auto kern = knorm_cluster_kernel<T, KPT>;
+    static PerDeviceOnce smem_set;  // one per <T, KPT> instantiation of this launcher
     cudaError_t e = ensure_dynamic_smem(kern, kClMaxSmem, smem_set);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -370,8 +401,12 @@ cudaError_t launch_knorm_cluster(const Dims& d, int dtype, const void* K, const 
                                  int32_t* idx_out, void* scores_out, cudaStream_t st) {
     ClusterPlan pl;
     if (!choose_cluster(d, &pl)) return cudaErrorNotSupported;
-    return (dtype == KVP_BF16) ? launch_cluster_t<__nv_bfloat16>(d, pl, K, V, K_out, V_out, idx_out, scores_out, st)
-                               : launch_cluster_t<__half>(d, pl, K, V, K_out, V_out, idx_out, scores_out, st);
+    if (d.S <= kClThreads * 12)
+        return (dtype == KVP_BF16) ? launch_cluster_t<__nv_bfloat16, 12>(d, pl, K, V, K_out, V_out, idx_out, scores_out, st)
+                                   : launch_cluster_t<__half, 12>(d, pl, K, V, K_out, V_out, idx_out, scores_out, st);
+    return (dtype == KVP_BF16)
+               ? launch_cluster_t<__nv_bfloat16, kClMaxKeysPerThread>(d, pl, K, V, K_out, V_out, idx_out, scores_out, st)
+               : launch_cluster_t<__half, kClMaxKeysPerThread>(d, pl, K, V, K_out, V_out, idx_out, scores_out, st);
 }
 
 }  // namespace kvp
