@@ -30,7 +30,24 @@ def u16(t: torch.Tensor) -> np.ndarray:
     return t.contiguous().view(torch.uint16).numpy()
 
 
-def make_case(name, *, B, Hq, Hkv, D, hidden, S, seed, dtype=torch.bfloat16, heavy_tail=False):
+CASES = {
+    "small64": dict(B=2, Hq=4, Hkv=2, D=64, hidden=256, S=384, seed=11),
+    "llama128": dict(B=1, Hq=8, Hkv=2, D=128, hidden=512, S=1200, seed=12),
+    "ties128": dict(B=1, Hq=4, Hkv=1, D=128, hidden=256, S=2500, seed=13, heavy_tail=True),
+    "half64": dict(B=1, Hq=2, Hkv=2, D=64, hidden=128, S=300, seed=14, dtype=torch.float16),
+}
+
+
+def make_case(name, **kw):
+    out = build_case(**kw)
+    np.savez_compressed(OUT / f"{name}.npz", **out)
+    print(name, {k: v.shape for k, v in out.items() if k.endswith("scores")})
+
+
+def build_case(*, B, Hq, Hkv, D, hidden, S, seed, dtype=torch.bfloat16, heavy_tail=False):
+    """Runs the imported reference on one seeded case and returns the arrays of its .npz (also used LIVE by
+    tests/test_oracle_golden.py: big bf16 GEMMs round differently on different host CPUs, so the stored files pin
+    the oracle bit-exactly only on a host whose GEMM kernels match the generating one)."""
     kvpress = import_reference()
     from transformers import LlamaConfig
     from transformers.models.llama.modeling_llama import LlamaAttention, LlamaRotaryEmbedding
@@ -110,8 +127,7 @@ def make_case(name, *, B, Hq, Hkv, D, hidden, S, seed, dtype=torch.bfloat16, hea
                 g = keys.gather(2, idx.unsqueeze(-1).expand(-1, -1, -1, D))
                 assert torch.equal(g, k2)
                 out[f"{tag}_kept_{i}"] = idx.sort(-1).values.numpy().astype(np.int32)
-    np.savez_compressed(OUT / f"{name}.npz", **out)
-    print(name, {k: v.shape for k, v in out.items() if k.endswith("scores")})
+    return out
 
 
 def make_decoding_table():
@@ -210,7 +226,13 @@ def tensor_checksum(*tensors) -> np.ndarray:
     return np.array([int(t.contiguous().view(torch.int16).to(torch.int64).sum()) for t in tensors], dtype=np.int64)
 
 
-def make_large(name="large32k", *, B=1, Hq=4, Hkv=1, D=128, hidden=256, S=32768, seed=21):
+def make_large(name="large32k", **kw):
+    out = build_large(**kw)
+    np.savez_compressed(OUT / f"{name}.npz", **out)
+    print(name, {k: v.shape for k, v in out.items() if k.endswith("scores")})
+
+
+def build_large(*, B=1, Hq=4, Hkv=1, D=128, hidden=256, S=32768, seed=21):
     """The four in-scope scorers + TOVA at a 32k context, reference run unmodified on CPU. Only the q_proj weight,
     the outputs and an input checksum are stored; K, V and the hidden states are regenerated from the seed."""
     kvpress = import_reference()
@@ -247,8 +269,7 @@ def make_large(name="large32k", *, B=1, Hq=4, Hkv=1, D=128, hidden=256, S=32768,
             for i, r in enumerate(ratios):
                 idx = sc.topk(int(S * (1 - r)), dim=-1).indices
                 out[f"{tag}_kept_{i}"] = idx.sort(-1).values.numpy().astype(np.int32)
-    np.savez_compressed(OUT / f"{name}.npz", **out)
-    print(name, {k: v.shape for k, v in out.items() if k.endswith("scores")})
+    return out
 
 
 if __name__ == "__main__":
@@ -261,10 +282,8 @@ if __name__ == "__main__":
     if "--rerotation-only" in sys.argv:
         make_rerotation()
         sys.exit(0)
-    make_case("small64", B=2, Hq=4, Hkv=2, D=64, hidden=256, S=384, seed=11)
-    make_case("llama128", B=1, Hq=8, Hkv=2, D=128, hidden=512, S=1200, seed=12)
-    make_case("ties128", B=1, Hq=4, Hkv=1, D=128, hidden=256, S=2500, seed=13, heavy_tail=True)
-    make_case("half64", B=1, Hq=2, Hkv=2, D=64, hidden=128, S=300, seed=14, dtype=torch.float16)
+    for case_name, case_kw in CASES.items():
+        make_case(case_name, **case_kw)
     make_decoding_table()
     make_rerotation()
     make_keydiff()

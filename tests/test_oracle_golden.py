@@ -2,10 +2,11 @@
 reference (tests/golden/make_golden.py). This is what pins the oracle; the GPU parity tests then
 compare the CUDA path against the oracle and against the same golden files."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import press_oracle as O
-from tests.conftest import GOLDEN_DIR, ulp16_diff
+from tests.conftest import GOLDEN_DIR, REFERENCE_DIR, assert_gemm_prologue, ulp16_diff
 
 
 def test_knorm_scores_match_reference(golden):
@@ -23,13 +24,17 @@ def test_streaming_scores_and_kept_sets(golden):
         assert torch.equal(ref_kept, want.expand_as(ref_kept))
 
 
-def test_snapkv_prologue_and_scores(golden):
+def test_snapkv_prologue_and_scores(golden_or_live):
+    golden = golden_or_live
     w, ksz = (int(x) for x in golden.z["snap_window"])
     q = O.snapkv_window_queries(golden.t("hidden_states"), golden.t("q_weight"), golden.Hq, golden.D,
                                 golden.t("cos"), golden.t("sin"), w)
-    assert torch.equal(q, golden.t("snap_q_window"))
-    got = O.snapkv_scores(q, golden.t("keys"), w, ksz)
-    assert torch.equal(got, golden.t("snap_scores"))
+    # the q_proj GEMM: bit-exact against the live reference, host-GEMM spread against a stored file
+    assert_gemm_prologue(q, golden.t("snap_q_window"), golden.live, "snap_q_window")
+    # the path proper, from the reference's own window queries: bit-exact on any host
+    assert torch.equal(O.snapkv_scores(golden.t("snap_q_window"), golden.t("keys"), w, ksz), golden.t("snap_scores"))
+    if golden.live:
+        assert torch.equal(O.snapkv_scores(q, golden.t("keys"), w, ksz), golden.t("snap_scores"))
 
 
 def test_snapkv_fp32_restatement_is_close_to_reference(golden):
@@ -41,11 +46,13 @@ def test_snapkv_fp32_restatement_is_close_to_reference(golden):
     assert rel.max() < 3e-2 and rel.mean() < 4e-3
 
 
-def test_expected_attention_stats_and_scores(golden):
+def test_expected_attention_stats_and_scores(golden_or_live):
+    golden = golden_or_live
     mu, cov = O.expected_attention_stats(golden.t("hidden_states"), golden.t("q_weight"), golden.Hq, golden.D,
                                          golden.t("ea_cos_future"), golden.t("ea_sin_future"), 4)
-    assert torch.equal(mu, golden.t("ea_mu"))
-    assert torch.equal(cov, golden.t("ea_cov"))
+    assert_gemm_prologue(mu, golden.t("ea_mu"), golden.live, "ea_mu")
+    assert_gemm_prologue(cov, golden.t("ea_cov"), golden.live, "ea_cov")
+    mu, cov = golden.t("ea_mu"), golden.t("ea_cov")     # the scan, from the reference's own statistics
     k, v = golden.t("keys"), golden.t("values")
     assert torch.equal(O.expected_attention_scores(k, v, mu, cov, 0.0, 4, True), golden.t("ea_scores"))
     assert torch.equal(O.expected_attention_scores(k, v, mu, None, 0.0, 4, False),
@@ -156,15 +163,31 @@ def test_keydiff_oracle_matches_reference_and_its_fp32_form():
             assert (hi.float() - ref_scores.float()).abs()[near_zero].max().item() < 2.0 ** -8
 
 
-def test_large32k_oracle_matches_reference():
+@pytest.mark.parametrize("live", [False, True], ids=["stored", "live"])
+def test_large32k_oracle_matches_reference(live):
     """S = 32768 (tests/golden/large32k.npz; inputs regenerated from the seed): the oracle restatements of Knorm, the
-    SnapKV / TOVA window attention, the ExpectedAttention prologue and scan are bit-exact at a long context too."""
+    SnapKV / TOVA window attention, the ExpectedAttention prologue and scan are bit-exact at a long context too.
+    `live` regenerates the arrays with the imported reference on this host (build container only): everything is
+    bit-exact there. Against the STORED file the stages downstream of a q_proj GEMM recomputed on this host may carry
+    another host's GEMM rounding (q is not stored at this size): bit-exact or <= 1 ulp on >= 99 % equal elements."""
     from transformers import LlamaConfig
     from transformers.models.llama.modeling_llama import LlamaRotaryEmbedding
 
-    from tests.golden.make_golden import large_inputs, tensor_checksum
+    from tests.golden.make_golden import build_large, large_inputs, tensor_checksum
 
-    z = np.load(GOLDEN_DIR / "large32k.npz")
+    if live:
+        if not REFERENCE_DIR.exists():
+            pytest.skip("no /root/reference here: live pinning runs in the build container only")
+        z = build_large()
+    else:
+        z = np.load(GOLDEN_DIR / "large32k.npz")
+
+    def after_q_proj(got, want, what):
+        if torch.equal(got, want):
+            return
+        assert not live, f"{what}: differs from the reference run live on this host"
+        d = ulp16_diff(got, want)
+        assert d.max().item() <= 1 and (d == 0).float().mean().item() >= 0.99, what
     B, Hq, Hkv, D, hidden, S, seed = (int(x) for x in z["meta"])
     h, k, v = large_inputs(seed, B, Hkv, S, D, hidden)
     assert (tensor_checksum(h, k, v) == z["checksum"]).all(), "torch CPU RNG no longer reproduces the seeded inputs"
@@ -179,13 +202,14 @@ def test_large32k_oracle_matches_reference():
     qw = t("q_weight")
     assert torch.equal(O.knorm_scores(k), t("knorm_scores"))
     q_last = O.snapkv_window_queries(h, qw, Hq, D, cos, sin, 1)[:, :, 0]
-    assert torch.equal(O.tova_scores(q_last, k), t("tova_scores"))
+    after_q_proj(O.tova_scores(q_last, k), t("tova_scores"), "tova_scores")
     q_win = O.snapkv_window_queries(h, qw, Hq, D, cos, sin, 64)
-    assert torch.equal(O.snapkv_scores(q_win, k, 64, 5), t("snap_scores"))
+    after_q_proj(O.snapkv_scores(q_win, k, 64, 5), t("snap_scores"), "snap_scores")
     cf, sf = rot(h, torch.arange(S, S + 512)[None])
     mu, cov = O.expected_attention_stats(h, qw, Hq, D, cf[0], sf[0], 4)
-    assert torch.equal(mu, t("ea_mu")) and torch.equal(cov, t("ea_cov"))
-    assert torch.equal(O.expected_attention_scores(k, v, mu, cov, 0.0, 4, True), t("ea_scores"))
+    assert_gemm_prologue(mu, t("ea_mu"), live, "ea_mu")
+    assert_gemm_prologue(cov, t("ea_cov"), live, "ea_cov")
+    assert torch.equal(O.expected_attention_scores(k, v, t("ea_mu"), t("ea_cov"), 0.0, 4, True), t("ea_scores"))
     for i, r in enumerate(z["ratios"]):
         n_kept = O.kept_count(S, float(r))
         for tag in ("knorm", "snap", "ea", "tova"):
