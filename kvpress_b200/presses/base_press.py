@@ -35,12 +35,13 @@ def _supported_models() -> tuple:
     return tuple(getattr(transformers, n) for n in names if hasattr(transformers, n))
 
 
-# Model classes the hooks are written for (same list as the reference, base_press.py:24-34). Shape limits of the
-# sm_100a library on top of that list: every scorer takes any head_dim that is a multiple of 8 (<= 256) EXCEPT the two
-# tensor-core scorers — SnapKVPress / PyramidKVPress and ExpectedAttentionPress with use_covariance=True — which need
-# head_dim 64 or 128, Hq/Hkv <= 8 and (Hq/Hkv) * window_size <= 512. Llama, Mistral, Qwen2 and Qwen3 checkpoints meet
-# them; Phi3 (head_dim 96) and Gemma3 (head_dim 256) raise "unsupported shape" for those two scorers — there is no
-# eager fallback by design (north_star: no CPU / multi-backend path).
+# Model classes the hooks are written for (same list as the reference, base_press.py:24-34). Shape coverage of the
+# sm_100a library on top of that list: every scorer takes any head_dim that is a multiple of 8 (<= 256); the two
+# tensor-core scorers — SnapKVPress / PyramidKVPress and ExpectedAttentionPress with use_covariance=True — are
+# instantiated for head_dim 64 / 128, Hq/Hkv <= 8 and (Hq/Hkv) * window_size <= 512 (Llama, Mistral, Qwen2, Qwen3).
+# Outside that set (Phi3: head_dim 96, Gemma3: 256) the C ABI returns "unsupported shape" and the presses evaluate the
+# SCORE stage with cuBLAS GEMMs on the GPU (kvpress_b200/wide_head_scores.py, logged once) while selection and
+# compaction stay on the sm_100a kernels. There is no CPU path anywhere.
 SUPPORTED_MODELS = _supported_models()
 
 

@@ -16,7 +16,7 @@ from dataclasses import dataclass
 import torch
 from torch import nn
 
-from kvpress_b200 import native
+from kvpress_b200 import native, wide_head_scores
 from kvpress_b200.presses.scorer_press import ScorerPress
 from kvpress_b200.utils import get_prerope_query_states
 
@@ -62,13 +62,27 @@ class ExpectedAttentionPress(ScorerPress):
     def score(self, module: nn.Module, hidden_states, keys: torch.Tensor, values, attentions, kwargs) -> torch.Tensor:
         assert keys.size(2) > self.n_sink, f"Input should contain more tokens than n_sink={self.n_sink}"
         mu, cov = self.get_query_statistics(module, hidden_states)
+        if not self._on_tensor_cores(keys, mu, cov):
+            return wide_head_scores.expected_attention_scores(keys, values, mu, cov, self.epsilon, self.n_sink,
+                                                              self.use_vnorm)
         return native.expected_attention_score(keys, values, mu, cov, self.epsilon, self.n_sink, self.use_vnorm)
+
+    @staticmethod
+    def _on_tensor_cores(keys: torch.Tensor, mu: torch.Tensor, cov) -> bool:
+        """False for shapes the sm_100a scan does not instantiate (covariance with head_dim other than 64 / 128, more
+        than 8 query heads per kv head): their score stage runs on cuBLAS GEMMs (wide_head_scores.py)."""
+        return wide_head_scores.expected_attention_on_tensor_cores(keys.shape[-1], mu.shape[1] // keys.shape[1],
+                                                                   cov is not None)
 
     def _fused_compress(self, module, hidden_states, keys, values, attentions, kwargs, n_kept):
         if self._score_is_overridden(ExpectedAttentionPress):
             return None
         assert keys.size(2) > self.n_sink, f"Input should contain more tokens than n_sink={self.n_sink}"
         mu, cov = self.get_query_statistics(module, hidden_states)
+        if not self._on_tensor_cores(keys, mu, cov):
+            scores = wide_head_scores.expected_attention_scores(keys, values, mu, cov, self.epsilon, self.n_sink,
+                                                                self.use_vnorm)
+            return native.scores_compress(scores, keys, values, n_kept)[:2]
         k_out, v_out, _, _ = native.expected_attention_compress(
             keys, values, mu, cov, self.epsilon, self.n_sink, self.use_vnorm, n_kept)
         return k_out, v_out

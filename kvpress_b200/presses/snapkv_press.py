@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import torch
 from torch import nn
 
-from kvpress_b200 import native
+from kvpress_b200 import native, wide_head_scores
 from kvpress_b200.presses.scorer_press import ScorerPress
 from kvpress_b200.utils import apply_rope, get_prerope_query_states
 
@@ -41,11 +41,22 @@ class SnapKVPress(ScorerPress):
 
     def score(self, module: nn.Module, hidden_states, keys: torch.Tensor, values, attentions, kwargs) -> torch.Tensor:
         q_window = self.window_queries(module, hidden_states, kwargs)
+        if not self._on_tensor_cores(keys, q_window):
+            return wide_head_scores.snapkv_scores(keys, q_window, self.window_size, self.kernel_size)
         return native.snapkv_score(keys, q_window, self.window_size, self.kernel_size)
+
+    def _on_tensor_cores(self, keys: torch.Tensor, q_window: torch.Tensor) -> bool:
+        """False for shapes the tcgen05 kernels do not instantiate (head_dim other than 64 / 128, more than 512
+        window-query rows per kv head): their score stage runs on cuBLAS GEMMs (wide_head_scores.py)."""
+        return wide_head_scores.snapkv_on_tensor_cores(keys.shape[-1], q_window.shape[1] // keys.shape[1],
+                                                       self.window_size)
 
     def _fused_compress(self, module, hidden_states, keys, values, attentions, kwargs, n_kept):
         if self._score_is_overridden(SnapKVPress):
             return None
         q_window = self.window_queries(module, hidden_states, kwargs)
+        if not self._on_tensor_cores(keys, q_window):
+            scores = wide_head_scores.snapkv_scores(keys, q_window, self.window_size, self.kernel_size)
+            return native.scores_compress(scores, keys, values, n_kept)[:2]
         k_out, v_out, _, _ = native.snapkv_compress(keys, values, q_window, self.window_size, self.kernel_size, n_kept)
         return k_out, v_out

@@ -360,8 +360,8 @@ def test_snapkv_any_group_size_and_window(G, w, D):
 
 
 def test_tensor_core_scorers_state_their_shape_limits():
-    """head_dim other than 64 / 128 (Phi3: 96, Gemma3: 256) has no tensor-core instantiation: a loud error, no
-    fallback."""
+    """head_dim other than 64 / 128 (Phi3: 96, Gemma3: 256) has no tensor-core instantiation: the C ABI says so with a
+    status code (no silent path inside the library); the presses route those shapes to the cuBLAS score stage (next test)."""
     nat = _native()
     k = torch.randn(1, 2, 600, 96, dtype=torch.bfloat16, device=DEV)
     mu = torch.randn(1, 4, 96, dtype=torch.bfloat16, device=DEV)
@@ -373,3 +373,42 @@ def test_tensor_core_scorers_state_their_shape_limits():
     # the covariance-free scan and every streaming scorer take any head_dim that is a multiple of 8
     assert nat.expected_attention_score(k, k, mu, None, 0.0, 4, False).shape == (1, 2, 600)
     assert nat.knorm_score(k).shape == (1, 2, 600)
+
+
+@pytest.mark.parametrize("D,Hq,Hkv", [(96, 4, 2), (256, 4, 1), (128, 16, 1)])
+def test_presses_on_head_dims_outside_the_tensor_core_set(D, Hq, Hkv):
+    """Phi-3 (head_dim 96), Gemma-3 (256), 16 query heads per kv head: the C ABI states the limit (test above), the
+    presses score those shapes with cuBLAS GEMMs on the GPU (kvpress_b200/wide_head_scores.py: fp32, one rounding) and
+    select + compact on the sm_100a kernels. Scores <= 1 ulp from the oracle's fp32 evaluation, kept rows == the
+    canonical selection of the press's own scores."""
+    from kvpress_b200 import ExpectedAttentionPress, SnapKVPress
+
+    torch.manual_seed(D + Hq)
+    B, S, hidden, w = 1, 1500, 256, 32
+    attn = _llama_attention(Hq, Hkv, D, hidden, torch.randn(Hq * D, hidden) * 0.05)
+    h = torch.randn(B, S, hidden).to(torch.bfloat16).to(DEV)
+    k = torch.randn(B, Hkv, S, D).to(torch.bfloat16).to(DEV)
+    v = torch.randn(B, Hkv, S, D).to(torch.bfloat16).to(DEV)
+    cos, sin = attn.rotary_emb(h, torch.arange(S, device=DEV)[None])
+    kwargs = {"position_embeddings": (cos, sin)}
+    with torch.no_grad():
+        snap = SnapKVPress(compression_ratio=0.5, window_size=w, kernel_size=5)
+        q_win = snap.window_queries(attn, h, kwargs)
+        sc = snap.score(attn, h, k, v, None, kwargs)
+        hi = O.snapkv_scores_fp32(q_win.cpu(), k.cpu(), w, 5).to(torch.bfloat16)
+        assert ulp16_diff(sc.cpu()[..., : S - w], hi[..., : S - w]).max() <= 1
+        k2, v2 = snap.compress(attn, h, k, v, None, kwargs)
+        want = O.select_lowest_index_ties(sc.cpu(), O.kept_count(S, 0.5))
+        assert (want[..., -w:] == torch.arange(S - w, S)).all()
+        assert torch.equal(k2.cpu(), O.gather_rows(k.cpu(), want)) and torch.equal(v2.cpu(), O.gather_rows(v.cpu(), want))
+
+        ea = ExpectedAttentionPress(compression_ratio=0.7)
+        mu, cov = ea.get_query_statistics(attn, h)
+        sc = ea.score(attn, h, k, v, None, kwargs)
+        hi = O.expected_attention_scores_fp32(k.cpu(), v.cpu(), mu.cpu().to(torch.bfloat16), cov.cpu().to(torch.bfloat16),
+                                              0.0, 4, True).to(torch.bfloat16)
+        assert ulp16_diff(sc.cpu()[..., 4:], hi[..., 4:]).max() <= 1
+        k2, v2 = ea.compress(attn, h, k, v, None, kwargs)
+        want = O.select_lowest_index_ties(sc.cpu(), O.kept_count(S, 0.7))
+        assert (want[..., :4] == torch.arange(4)).all()
+        assert torch.equal(k2.cpu(), O.gather_rows(k.cpu(), want)) and torch.equal(v2.cpu(), O.gather_rows(v.cpu(), want))

@@ -393,3 +393,50 @@ def test_adakv_fake_keys_equal_an_explicit_per_head_mask(backend, model):
     y_plain = model.model(input_ids=ids[:, :1], past_key_values=copy.deepcopy(cache)).last_hidden_state
     assert torch.allclose(y_patch, y_mask, atol=1e-5)
     assert not torch.allclose(y_patch, y_plain, atol=1e-4)
+
+
+# ---- shapes outside the tcgen05 instantiations: cuBLAS score stage (kvpress_b200/wide_head_scores.py) ----------------
+def test_wide_head_shape_predicates():
+    from kvpress_b200 import wide_head_scores as W
+
+    assert W.snapkv_on_tensor_cores(128, 4, 64) and W.snapkv_on_tensor_cores(64, 8, 64)
+    assert not W.snapkv_on_tensor_cores(96, 1, 64) and not W.snapkv_on_tensor_cores(256, 2, 64)
+    assert not W.snapkv_on_tensor_cores(128, 16, 64)                      # 1024 window-query rows per kv head
+    assert W.expected_attention_on_tensor_cores(96, 3, False)             # the covariance-free scan takes any head_dim
+    assert not W.expected_attention_on_tensor_cores(96, 1, True) and not W.expected_attention_on_tensor_cores(128, 16, False)
+
+
+def test_wide_head_scores_refuse_cpu_tensors():
+    from kvpress_b200 import wide_head_scores as W
+
+    k = torch.randn(1, 1, 40, 96).to(torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        W.snapkv_scores(k, k[:, :, -8:], 8, 5)
+
+
+@pytest.mark.parametrize("D,G,dtype", [(96, 1, torch.bfloat16), (256, 2, torch.bfloat16), (96, 3, torch.float16)])
+def test_wide_head_score_math_is_the_fp32_formula_rounded_once(monkeypatch, D, G, dtype):
+    """The arithmetic of the cuBLAS score stage (device check lifted for the CPU box) against the oracle's fp32
+    evaluation of the reference formulas: <= 1 ulp of the 16-bit score, forced positions carry max + 1."""
+    from kvpress_b200 import wide_head_scores as W
+    from oracle import press_oracle as O
+    from tests.conftest import ulp16_diff
+
+    monkeypatch.setattr(W, "_require_cuda", lambda t: None)
+    torch.manual_seed(D + G)
+    B, Hkv, S, w = 2, 2, 300, 16
+    k = torch.randn(B, Hkv, S, D).to(dtype)
+    v = torch.randn(B, Hkv, S, D).to(dtype)
+    q = (torch.randn(B, Hkv * G, w, D) * 0.5).to(dtype)
+    got = W.snapkv_scores(k, q, w, 5, chunk=128)
+    want = O.snapkv_scores_fp32(q, k, w, 5).to(dtype)
+    assert ulp16_diff(got[..., :-w], want[..., :-w]).max().item() <= 1
+    assert (got[..., -w:] == (got[..., :-w].float().max() + 1).to(dtype)).all()
+    mu = (torch.randn(B, Hkv * G, D) * 0.3).to(dtype)
+    a = torch.randn(B, Hkv * G, D, D) / D ** 0.5
+    cov = (a @ a.transpose(-1, -2) * 0.5).to(dtype)
+    for c, eps, vn in ((cov, 0.0, True), (None, 0.0, False), (cov, 1e-2, True)):
+        got = W.expected_attention_scores(k, v, mu, c, eps, 4, vn, chunk=64)
+        want = O.expected_attention_scores_fp32(k, v, mu, c, eps, 4, vn).to(dtype)
+        assert ulp16_diff(got[..., 4:], want[..., 4:]).max().item() <= 1
+        assert (got[..., :4] == (got[..., 4:].float().max() + 1).to(dtype)).all()
