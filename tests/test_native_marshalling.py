@@ -47,6 +47,11 @@ def rec(monkeypatch):
     monkeypatch.setattr(native, "_out_device", lambda keys: keys.device)
     monkeypatch.setattr(native, "_normalise", lambda t: t if native._rows_ok(t) else t.contiguous())  # CPU stands in for CUDA
     monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    # the recorder accepts any shape: keep the tiny head_dim-16 inputs of these tests on the C-ABI entry points
+    from kvpress_b200 import wide_head_scores
+
+    monkeypatch.setattr(wide_head_scores, "snapkv_on_tensor_cores", lambda *a: True)
+    monkeypatch.setattr(wide_head_scores, "expected_attention_on_tensor_cores", lambda *a: True)
     return r
 
 
