@@ -19,6 +19,7 @@
 //       fp32, rounds it ONCE to the cache dtype, and emits keys + histogram for the select stage.
 // Covariance-free mode (use_covariance=False) is a plain streaming GEMV kernel.
 #include <mutex>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "knorm_chunk.cuh"
@@ -548,6 +549,400 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     if (warp == 2) umma::tmem_dealloc(tmem, 512);
 }
 
+// ======================================================================================================================
+// CTA-PAIR variant (cta_group::2, thread-block cluster of two): the default for even group sizes.
+//
+// Why: with both operands in shared memory an M128 x N256 x K16 MMA reads (128 + 256) x 32 B = 12 KB per 128 nominal
+// cycles; the one-CTA kernel above issues them at ~180 cycles each with or without epilogue work
+// (profiles/r02_ea_experiments.txt, r02_ea_roles*.txt) — the operand fetch, not the tensor pipe, sets its pace. A CTA
+// pair runs ONE MMA of M = 256 over two consecutive K tiles: each CTA feeds its own 128 rows of A and only ITS half of
+// B (one head's covariance instead of two), 8 KB per MMA and SM. The freed shared memory holds the covariance of a
+// second head pair, so a K tile is staged once for four heads (two MMA halves per tile) instead of once per head pair.
+//
+// Work: unit = (row, group of 2*NH heads); item = (unit, pair of consecutive 128-position tiles). The items are cut
+// into equal contiguous ranges, one per CTA pair (any number of pairs; a range may cross a unit boundary). CTA `c` of
+// the pair owns tile 2*tp + c of item tp: stages it (TMA, completion counted on the LEADER's barrier), holds
+// the covariance of head 2*half + c of each half, reads its 128 x N accumulator rows from its own tensor memory and
+// finishes them exactly like the one-CTA kernel. Only the leader issues MMAs; its commits arrive on the barriers of
+// both CTAs; the peer's epilogue releases accumulator buffers on the leader's barrier.
+template <int D, int NH>
+struct Ea2Smem {
+    static constexpr int kPanels = D / 64;
+    static constexpr int kCovHeadPanel = D * 128;                 // one head's [D rows x 64 columns] panel
+    static constexpr int kCovBytes = NH * kPanels * kCovHeadPanel;  // this CTA's share: one head per half
+    static constexpr int kStageBytes = kPanels * kEaTile * 128;
+    static constexpr int kVStages = 1;
+    static constexpr int kAxBytes = kEaTile * 32;
+    static constexpr int kBxBytes = NH * D * 32;                  // bias rows of this CTA's heads
+    static constexpr int kFixedBytes = kCovBytes + kAxBytes + kBxBytes + 512 + kVStages * kStageBytes;
+    static constexpr int kFit = (227 * 1024 - 1024 - kFixedBytes) / kStageBytes;
+    static constexpr int kStages = kFit >= 4 ? 4 : kFit;
+    static_assert(kStages >= 2, "K ring needs two stages");
+    static constexpr int kCovOff = 0;
+    static constexpr int kStageOff = kCovBytes;
+    static constexpr int kVStageOff = kStageOff + kStages * kStageBytes;
+    static constexpr int kAxOff = kVStageOff + kVStages * kStageBytes;
+    static constexpr int kBxOff = kAxOff + kAxBytes;
+    static constexpr int kBarOff = kBxOff + kBxBytes;
+    static constexpr int kTotal = kBarOff + 512;
+    static_assert(kTotal + 1024 <= 227 * 1024, "shared memory budget");
+};
+
+// contiguous, balanced item ranges: pair p owns [ea2_start(p), ea2_start(p + 1))
+__host__ __device__ inline long long ea2_start(int p, long long total, int n_pairs) {
+    return ((long long)p * total) / n_pairs;
+}
+// the pair whose (non-empty) range contains `item`
+__host__ __device__ inline int ea2_pair_of(long long item, long long total, int n_pairs) {
+    int p = (int)((item * n_pairs) / total);
+    if (p >= n_pairs) p = n_pairs - 1;
+    while (p + 1 < n_pairs && ea2_start(p + 1, total, n_pairs) <= item) ++p;
+    while (p > 0 && ea2_start(p, total, n_pairs) > item) --p;
+    return p;
+}
+
+template <typename T, int D, int NH>
+__global__ void __launch_bounds__(512, 1)
+ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapCov,
+                      const __grid_constant__ CUtensorMap mapV, const T* __restrict__ mu, int H, int Hq, int S,
+                      int n_sink, int R, int n_tiles128, int n_tp, int n_pairs, int n_parts, EaScratch sc, int S_pad,
+                      int g_total, int n_split, int do_vnorm) {
+    using L = Ea2Smem<D, NH>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // same offset in both CTAs of the pair
+    unsigned char* s_cov = smem + L::kCovOff;
+    unsigned char* s_stage = smem + L::kStageOff;
+    unsigned char* s_vstage = smem + L::kVStageOff;
+    unsigned char* s_ax = smem + L::kAxOff;
+    unsigned char* s_bx = smem + L::kBxOff;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+    constexpr int kStages = L::kStages;
+    uint64_t* k_full = bars;          // [kStages]  used in the leader only: both CTAs' tiles have landed
+    uint64_t* k_empty = bars + 4;     // [kStages]  per CTA: MMA commit + the warps that read this CTA's k rows
+    uint64_t* t_full = bars + 8;      // [2]        per CTA: MMA commit (multicast)
+    uint64_t* t_empty = bars + 10;    // [2]        used in the leader only: 4 warps of each CTA drained the buffer
+    uint64_t* cov_full = bars + 12;   // [1]        used in the leader only
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* v_full = bars + 14;     // [1]        per CTA
+    uint64_t* v_empty = bars + 16;    // [1]        per CTA
+    float* s_red = reinterpret_cast<float*>(bars + 18);  // [8 warps][2 head slots][2]
+
+    constexpr int HPH = 2;            // heads per half: head 2*half + c lives in CTA c
+    constexpr int kN = HPH * D;       // MMA N (both CTAs together)
+    constexpr int kBufCols = 256;
+    constexpr int G = 2 * NH;         // heads of a unit
+    static_assert(kN <= 256, "two heads must fit one MMA");
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = (int)umma::cluster_ctarank();
+    const bool leader = c == 0;
+    const int P = blockIdx.x >> 1;
+
+    if (tid == 0) {
+        umma::prefetch_tmap(&mapK);
+        umma::prefetch_tmap(&mapCov);
+        if (do_vnorm) umma::prefetch_tmap(&mapV);
+        for (int i = 0; i < kStages; ++i) {
+            umma::mbar_init(&k_full[i], 1);
+            umma::mbar_init(&k_empty[i], 1 + 4 * NH);  // MMA commit + the epilogue warps that read the tile's k rows
+        }
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(&t_full[i], 1);
+            umma::mbar_init(&t_empty[i], 8);            // 4 warps of the draining warpgroup in EACH CTA
+        }
+        umma::mbar_init(&v_full[0], 1);
+        umma::mbar_init(&v_empty[0], 4);
+        umma::mbar_init(cov_full, 1);
+        umma::mbar_fence_init();
+    }
+    if (warp == 2) umma::tmem_alloc_pair(tmem_slot, 512);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::cluster_sync();  // both CTAs' barriers exist before any remote arrival / transaction
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const float inv_2d = 1.0f / (2.0f * (float)D);
+    const float bias_scale = 2.0f * sqrtf((float)D);
+    const long long total = (long long)R * n_split * n_tp;
+    const long long i_begin = ea2_start(P, total, n_pairs), i_end = ea2_start(P + 1, total, n_pairs);
+
+    uint32_t k_it = 0, h_it = 0, cov_it = 0, v_it = 0;  // pipeline state of this role, carried across units
+
+    for (long long it = i_begin; it < i_end;) {
+        const int unit = (int)(it / n_tp);
+        const int tp_begin = (int)(it - (long long)unit * n_tp);
+        const int tp_end = (int)min((long long)n_tp, tp_begin + (i_end - it));
+        it += tp_end - tp_begin;
+        const int row = unit / n_split, hp = unit % n_split, g_off = hp * G;
+        const int b = row / H, h = row % H;
+        const int hq0 = b * Hq + h * g_total + g_off;  // first head of the unit in [B*Hq]
+        const bool v_active = do_vnorm != 0;
+        // this CTA's slot among the partial softmax statistics of the unit
+        const long long unit_first = (long long)unit * n_tp;
+        const int first_pair = ea2_pair_of(unit_first, total, n_pairs);
+        const int part = 2 * (P - first_pair) + c;
+
+        // ---- unit prologue: both CTAs are done with the previous unit (every MMA that read either CTA's shared
+        // memory has completed: each epilogue waited for the accumulators of all its tiles) ---------------------------
+        __syncthreads();
+        umma::cluster_sync();
+        for (int n = tid; n < NH * D; n += kEaThreads) {
+            // bias row n of this CTA: half n / D, head 2 * half + c, element n % D
+            const int g = 2 * (n / D) + c;
+            const float bias = bias_scale * F16Traits<T>::to_float(
+                                                reinterpret_cast<const uint16_t*>(mu)[(size_t)(hq0 + g) * D + (n % D)]);
+            const uint16_t hi = F16Traits<T>::from_float(bias);
+            const uint16_t lo = F16Traits<T>::from_float(bias - F16Traits<T>::to_float(hi));
+            *reinterpret_cast<uint4*>(s_bx + umma::k16_noswizzle_offset(n, 0)) =
+                make_uint4((uint32_t)hi | ((uint32_t)lo << 16), 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(s_bx + umma::k16_noswizzle_offset(n, 1)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (tid < kEaTile) {
+            const uint32_t one = (uint32_t)F16Traits<T>::from_float(1.0f);
+            *reinterpret_cast<uint4*>(s_ax + umma::k16_noswizzle_offset(tid, 0)) =
+                make_uint4(one | (one << 16), 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(s_ax + umma::k16_noswizzle_offset(tid, 1)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> UMMA reads
+        __syncthreads();
+        umma::cluster_sync();  // the peer's bias / ones operands are in place before the leader issues
+
+        if (warp == 0) {
+            // ===== TMA producer (both CTAs, own tiles; bytes counted on the leader's barriers) =====
+            if (lane == 0) {
+                if (leader) umma::mbar_arrive_expect_tx(cov_full, 2 * L::kCovBytes);
+                for (int kp = 0; kp < L::kPanels; ++kp)
+                    for (int half = 0; half < NH; ++half)
+                        umma::tma_load_3d_pair(s_cov + (kp * NH + half) * L::kCovHeadPanel, &mapCov, cov_full,
+                                               kp * 64, 0, hq0 + 2 * half + c);
+                for (int tp = tp_begin; tp < tp_end; ++tp, ++k_it) {
+                    const int stage = k_it % kStages;
+                    { EA_T0(); umma::mbar_wait(&k_empty[stage], ((k_it / kStages) & 1) ^ 1); EA_ACC(0); }
+                    if (leader) umma::mbar_arrive_expect_tx(&k_full[stage], 2 * L::kStageBytes);
+                    for (int kp = 0; kp < L::kPanels; ++kp)
+                        umma::tma_load_4d_pair(s_stage + stage * L::kStageBytes + kp * (kEaTile * 128), &mapK,
+                                               &k_full[stage], kp * 64, (2 * tp + c) * kEaTile, h, b);
+                }
+            }
+        } else if (warp == 3) {
+            // ===== V producer (own tile, CTA-local barriers) =====
+            if (lane == 0 && v_active) {
+                for (int tp = tp_begin; tp < tp_end; ++tp) {
+                    if ((tp % n_split) != hp) continue;   // the units of a row take turns
+                    umma::mbar_wait(&v_empty[0], (v_it & 1) ^ 1);
+                    umma::mbar_arrive_expect_tx(&v_full[0], L::kStageBytes);
+                    for (int kp = 0; kp < L::kPanels; ++kp)
+                        umma::tma_load_4d(s_vstage + kp * (kEaTile * 128), &mapV, &v_full[0], kp * 64,
+                                          (2 * tp + c) * kEaTile, h, b);
+                    ++v_it;
+                }
+            }
+        } else if (warp == 1) {
+            // ===== MMA issuer (leader only) =====
+            if (lane == 0 && leader) {
+                const uint32_t idesc = umma::instr_desc_f16(2 * kEaTile, kN, F16Traits<T>::kMmaFormat);
+                umma::mbar_wait(cov_full, cov_it & 1);
+                for (int tp = tp_begin; tp < tp_end; ++tp, ++k_it) {
+                    const int stage = k_it % kStages;
+                    { EA_T0(); umma::mbar_wait(&k_full[stage], (k_it / kStages) & 1); EA_ACC(1); }
+                    umma::fence_after_sync();
+                    const uint32_t a_base = umma::smem_u32(s_stage + stage * L::kStageBytes);
+#pragma unroll 1
+                    for (int half = 0; half < NH; ++half, ++h_it) {
+                        const int buf = h_it & 1;
+                        { EA_T0(); umma::mbar_wait(&t_empty[buf], ((h_it >> 1) & 1) ^ 1); EA_ACC(2); }
+                        umma::fence_after_sync();
+#pragma unroll
+                        for (int k = 0; k < D / 16; ++k) {
+                            const int kp = k >> 2, kk = k & 3;
+                            const uint64_t da = umma::smem_desc_sw128(a_base + kp * (kEaTile * 128) + kk * 32);
+                            const uint64_t db = umma::smem_desc_sw128(
+                                umma::smem_u32(s_cov + (kp * NH + half) * L::kCovHeadPanel) + kk * 32);
+                            umma::mma_f16_ss_pair(tmem + buf * kBufCols, da, db, idesc, k > 0);
+                        }
+                        umma::mma_f16_ss_pair(tmem + buf * kBufCols,
+                                              umma::smem_desc_k16_noswizzle(umma::smem_u32(s_ax)),
+                                              umma::smem_desc_k16_noswizzle(umma::smem_u32(s_bx) + (half * D / 8) * 256),
+                                              idesc, 1);
+                        umma::mma_commit_pair(&t_full[buf]);
+                    }
+                    umma::mma_commit_pair(&k_empty[stage]);
+                }
+            }
+            ++cov_it;
+        } else if (warp >= 4 && warp < 12) {
+            // ===== epilogue (both CTAs): warpgroup wg drains TMEM buffer wg; thread = key row of THIS CTA's tile =====
+            const int wg = (warp - 4) >> 2;
+            const int ew = warp & 3;
+            const int r = ew * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+            float run_m[HPH], run_z[HPH];
+#pragma unroll
+            for (int q = 0; q < HPH; ++q) {
+                run_m[q] = -INFINITY;
+                run_z[q] = 0.f;
+            }
+            for (int tp = tp_begin; tp < tp_end; ++tp, ++k_it) {
+                const int stage = k_it % kStages;
+                const unsigned char* krow = s_stage + stage * L::kStageBytes;
+                const int s = (2 * tp + c) * kEaTile + r;
+                const bool valid = (s >= n_sink) && (s < S);
+                if (v_active && (tp % n_split) == hp) {
+                    // value norms of this CTA's tile: both warpgroups observe every V phase (one V stage), one of them
+                    // reads — the warpgroup without an accumulator for this tile (NH = 1), or alternately (NH = 2)
+                    umma::mbar_wait(&v_full[0], v_it & 1);
+                    const bool reader = (NH == 1) ? ((int)(h_it & 1) != wg) : ((int)(v_it & 1) == wg);
+                    if (reader) {
+                        float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+                        for (int c8 = 0; c8 < D / 8; ++c8) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(
+                                s_vstage + (c8 >> 3) * (kEaTile * 128) + umma::sw128_offset(r, c8 & 7));
+                            const float2 f0 = F16Traits<T>::unpack2(v.x), f1 = F16Traits<T>::unpack2(v.y);
+                            const float2 f2 = F16Traits<T>::unpack2(v.z), f3 = F16Traits<T>::unpack2(v.w);
+                            ss0 = fmaf(f0.x, f0.x, ss0); ss1 = fmaf(f0.y, f0.y, ss1);
+                            ss0 = fmaf(f1.x, f1.x, ss0); ss1 = fmaf(f1.y, f1.y, ss1);
+                            ss0 = fmaf(f2.x, f2.x, ss0); ss1 = fmaf(f2.y, f2.y, ss1);
+                            ss0 = fmaf(f3.x, f3.x, ss0); ss1 = fmaf(f3.y, f3.y, ss1);
+                        }
+                        __syncwarp();
+                        if (lane == 0) umma::mbar_arrive(&v_empty[0]);
+                        if (s < S) sc.vnorm[(size_t)row * S_pad + s] = sqrtf(ss0 + ss1);
+                    }
+                    ++v_it;
+                }
+#pragma unroll 1
+                for (int half = 0; half < NH; ++half, ++h_it) {
+                    const int buf = h_it & 1;
+                    if (buf != wg) continue;
+                    {
+                        EA_T0();
+                        umma::mbar_wait(&t_full[buf], (h_it >> 1) & 1);  // implies: both K tiles landed and were consumed
+                        if (warp == 4 && lane == 0) EA_ACC(4);
+                    }
+                    EA_T0();
+                    umma::fence_after_sync();
+                    const uint32_t tbase = tmem + lane_base + buf * kBufCols;
+                    uint64_t acc2[HPH][4];
+#pragma unroll
+                    for (int q = 0; q < HPH; ++q)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc2[q][j] = 0ull;
+                    constexpr int kC16 = D / 16;
+                    uint32_t y[2][16];
+                    umma::tmem_ld16(tbase, y[0]);
+#pragma unroll
+                    for (int cc = 0; cc < kC16; ++cc) {
+                        uint64_t k2[8];
+                        {
+                            const int c0 = cc * 16;
+                            const int kpanel = c0 >> 6;
+#pragma unroll
+                            for (int ch = 0; ch < 2; ++ch) {
+                                const uint4 v = *reinterpret_cast<const uint4*>(
+                                    krow + kpanel * (kEaTile * 128) + umma::sw128_offset(r, ((c0 & 63) >> 3) + ch));
+                                k2[ch * 4] = pack_f32x2(F16Traits<T>::unpack2(v.x));
+                                k2[ch * 4 + 1] = pack_f32x2(F16Traits<T>::unpack2(v.y));
+                                k2[ch * 4 + 2] = pack_f32x2(F16Traits<T>::unpack2(v.z));
+                                k2[ch * 4 + 3] = pack_f32x2(F16Traits<T>::unpack2(v.w));
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < HPH; ++q) {
+                            constexpr int kSteps = kC16 * HPH;
+                            const int step = cc * HPH + q;
+                            umma::tmem_ld_wait();
+                            if (step + 1 < kSteps) {
+                                const int cn = (step + 1) / HPH, qn = (step + 1) % HPH;
+                                umma::tmem_ld16(tbase + qn * D + cn * 16, y[(step + 1) & 1]);
+                            }
+                            const uint32_t* yy = y[step & 1];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                acc2[q][j & 3] = fma_f32x2(k2[j], pack_u32x2(yy[2 * j], yy[2 * j + 1]), acc2[q][j & 3]);
+                        }
+                    }
+                    float acc[HPH];
+#pragma unroll
+                    for (int q = 0; q < HPH; ++q) {
+                        const float2 a0 = unpack_f32x2(acc2[q][0]), a1 = unpack_f32x2(acc2[q][1]);
+                        const float2 a2 = unpack_f32x2(acc2[q][2]), a3 = unpack_f32x2(acc2[q][3]);
+                        acc[q] = ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+                    }
+                    if (warp == 4 && lane == 0) EA_ACC(5);
+                    umma::fence_before_sync();
+                    __syncwarp();
+                    // release before the global stores (an arrive has release semantics): the accumulator buffer on the
+                    // LEADER's barrier, this CTA's K stage on its own
+                    if (lane == 0) {
+                        umma::mbar_arrive_leader(&t_empty[buf]);
+                        umma::mbar_arrive(&k_empty[stage]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < HPH; ++q) {
+                        const int g = half * HPH + q;
+                        const float lg = acc[q] * inv_2d;
+                        if (valid) {
+                            sc.logits[((size_t)row * g_total + g_off + g) * S_pad + s] = lg;
+                            const float m_new = fmaxf(run_m[q], lg);
+                            run_z[q] = run_z[q] * __expf(run_m[q] - m_new) + __expf(lg - m_new);
+                            run_m[q] = m_new;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- warp-level (max, sum-exp) per head slot -> shared ---------------------------------------------------
+#pragma unroll
+            for (int q = 0; q < HPH; ++q) {
+                float m = run_m[q], z = run_z[q];
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const float m2 = __shfl_xor_sync(0xFFFFFFFFu, m, off);
+                    const float z2 = __shfl_xor_sync(0xFFFFFFFFu, z, off);
+                    const float mn = fmaxf(m, m2);
+                    z = (mn == -INFINITY) ? 0.f : z * __expf(m - mn) + z2 * __expf(m2 - mn);
+                    m = mn;
+                }
+                if (lane == 0) {
+                    s_red[((warp - 4) * 2 + q) * 2] = m;
+                    s_red[((warp - 4) * 2 + q) * 2 + 1] = z;
+                }
+            }
+        }
+        // ---- CTA-level softmax statistics of this CTA's tiles -> partial[row][g][part] -------------------------------
+        __syncthreads();
+        if (tid < G) {
+            // head g sat in slot g % 2 of: the warps of warpgroup g / 2 (NH = 2: one half per warpgroup) or of both
+            // warpgroups (NH = 1: tiles alternate)
+            const int g = tid, q = g % HPH;
+            float m = -INFINITY, z = 0.f;
+            for (int w = 0; w < 8; ++w) {
+                if (NH == 2 && (w >> 2) != g / HPH) continue;
+                const float m2 = s_red[(w * 2 + q) * 2], z2 = s_red[(w * 2 + q) * 2 + 1];
+                const float mn = fmaxf(m, m2);
+                z = (mn == -INFINITY) ? 0.f : z * __expf(m - mn) + z2 * __expf(m2 - mn);
+                m = mn;
+            }
+            sc.partial[((size_t)row * g_total + g_off + g) * n_parts + part] = make_float2(m, z);
+        }
+        if (part == 0 && tid >= 32 && tid < 32 + G) {
+            // the unit's first CTA neutralises the slots no CTA of this unit owns (units take a varying number of pairs)
+            const long long unit_last = unit_first + n_tp - 1;
+            const int used = 2 * (ea2_pair_of(unit_last, total, n_pairs) - first_pair + 1);
+            for (int p = used; p < n_parts; ++p)
+                sc.partial[((size_t)row * g_total + g_off + (tid - 32)) * n_parts + p] = make_float2(-INFINITY, 0.f);
+        }
+    }
+
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::cluster_sync();  // the peer may still be reading its accumulators / this CTA's barriers
+    if (warp == 2) umma::tmem_dealloc_pair(tmem, 512);
+}
+
 // ---- covariance-free logits: mu.k / sqrt(d) with plain streaming loads (use_covariance=False) -------
 template <typename T, int LPR>
 __global__ void __launch_bounds__(256)
@@ -884,6 +1279,95 @@ static cudaError_t launch_ea_logits_t(const Dims& d, const void* K, const void* 
     return cudaPeekAtLastError();
 }
 
+// ---- host launcher of the CTA-pair kernel ---------------------------------------------------------------------------
+template <typename T, int D, int NH>
+static cudaError_t launch_ea_logits_pair_t(const Dims& d, const void* K, const void* V_or_null, const void* mu,
+                                           const void* cov, int n_sink, const Workspace& ws, const EaScratch& sc,
+                                           int* n_parts_out, cudaStream_t st) {
+    using L = Ea2Smem<D, NH>;
+    const int n_tiles128 = (d.S + kEaTile - 1) / kEaTile;
+    const int n_tp = (n_tiles128 + 1) / 2;
+    const int g_total = d.Hq / d.H;
+    const int n_split = g_total / (2 * NH);
+    const long long total = (long long)d.R * n_split * n_tp;
+
+    const int smem = L::kTotal + 1024;
+    auto kern = ea_logits_pair_kernel<T, D, NH>;
+    static PerDeviceOnce smem_set;  // one per <T, D, NH> instantiation of this launcher
+    cudaError_t e = ensure_dynamic_smem(kern, smem, smem_set);
+    if (e != cudaSuccess) return e;
+
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.blockDim = dim3(kEaThreads, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    // co-resident CTA pairs (a GPC with an odd SM count leaves one SM unpaired): queried once per device
+    static PerDeviceInt max_pairs;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    if (max_pairs.v[dev] == 0) {
+        cfg.gridDim = dim3(2 * (device_sm_count() / 2), 1, 1);
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+            (void)cudaGetLastError();
+            n = device_sm_count() / 2;
+        }
+        max_pairs.v[dev] = n;
+    }
+    int n_pairs = max_pairs.v[dev];
+    if (n_pairs > kEaMaxParts / 2) n_pairs = kEaMaxParts / 2;
+    if ((long long)n_pairs > total) n_pairs = (int)total;  // every pair owns at least one item
+    // slots of the per-CTA softmax partials of a unit: two per pair that touches it
+    int max_count = 1;
+    for (int u = 0; u < d.R * n_split; ++u) {
+        const int first = ea2_pair_of((long long)u * n_tp, total, n_pairs);
+        const int last = ea2_pair_of((long long)(u + 1) * n_tp - 1, total, n_pairs);
+        if (last - first + 1 > max_count) max_count = last - first + 1;
+    }
+    const int n_parts = 2 * max_count;
+    *n_parts_out = n_parts;
+
+    CUtensorMap mapK, mapCov, mapV;
+    const bool in_kernel_v = V_or_null != nullptr;
+    {  // V tiles are staged exactly like K tiles (same box, same swizzle), from V's own strides
+        const void* base = in_kernel_v ? V_or_null : K;
+        const Strides3& xs = in_kernel_v ? d.vs : d.ks;
+        const uint64_t row_b = (uint64_t)xs.s * 2;
+        const uint64_t h_b = d.H > 1 ? (uint64_t)xs.h * 2 : row_b * (uint64_t)d.S;
+        const uint64_t b_b = d.B > 1 ? (uint64_t)xs.b * 2 : h_b * (uint64_t)d.H;
+        const uint64_t dims[4] = {(uint64_t)D, (uint64_t)d.S, (uint64_t)d.H, (uint64_t)d.B};
+        const uint64_t str[4] = {0, row_b, h_b, b_b};
+        const uint32_t box[4] = {64, (uint32_t)kEaTile, 1, 1};
+        if ((e = make_tmap_16bit(&mapV, base, 4, dims, str, box)) != cudaSuccess) return e;
+    }
+    {
+        const uint64_t row_b = (uint64_t)d.ks.s * 2;
+        const uint64_t h_b = d.H > 1 ? (uint64_t)d.ks.h * 2 : row_b * (uint64_t)d.S;
+        const uint64_t b_b = d.B > 1 ? (uint64_t)d.ks.b * 2 : h_b * (uint64_t)d.H;
+        const uint64_t dims[4] = {(uint64_t)D, (uint64_t)d.S, (uint64_t)d.H, (uint64_t)d.B};
+        const uint64_t str[4] = {0, row_b, h_b, b_b};
+        const uint32_t box[4] = {64, (uint32_t)kEaTile, 1, 1};
+        if ((e = make_tmap_16bit(&mapK, K, 4, dims, str, box)) != cudaSuccess) return e;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)D, (uint64_t)D, (uint64_t)d.B * d.Hq};
+        const uint64_t str[3] = {0, (uint64_t)D * 2, (uint64_t)D * D * 2};
+        const uint32_t box[3] = {64, (uint32_t)D, 1};
+        if ((e = make_tmap_16bit(&mapCov, cov, 3, dims, str, box)) != cudaSuccess) return e;
+    }
+    cfg.gridDim = dim3(2 * n_pairs, 1, 1);
+    return cudaLaunchKernelEx(&cfg, kern, mapK, mapCov, mapV, static_cast<const T*>(mu), d.H, d.Hq, d.S, n_sink, d.R,
+                              n_tiles128, n_tp, n_pairs, n_parts, sc, (int)ws.S_pad, g_total, n_split,
+                              in_kernel_v ? 1 : 0);
+}
+
 // Side stream + fork/join events for the concurrent V-norm kernel: created once per device, never
 // modified afterwards (the only process-wide state of the library besides cached device properties).
 struct EaSideStream {
@@ -942,7 +1426,14 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
 #define KVP_EA_RESIDENT_HEADS 2  // A/B knob: 4 = round-1 layout (all four heads of a Llama-3.1-8B group in one CTA)
 #endif
     const bool tc_path = cov != nullptr && (d.D == 128 || d.D == 64);
-    const bool in_kernel_v = KVP_EA_V_STAGES > 0 && use_vnorm && tc_path && (G <= 2 || KVP_EA_RESIDENT_HEADS == 2);
+    // CTA-pair kernel (cta_group::2) for even group sizes; KVP_EA_PAIR=0 keeps the one-CTA kernel (A/B, odd groups)
+    static const bool pair_knob = [] {
+        const char* v = getenv("KVP_EA_PAIR");
+        return !(v && *v) || atoi(v) != 0;
+    }();
+    const bool pair_path = pair_knob && tc_path && G % 2 == 0;
+    const bool in_kernel_v = use_vnorm && tc_path &&
+                             (pair_path || (KVP_EA_V_STAGES > 0 && (G <= 2 || KVP_EA_RESIDENT_HEADS == 2)));
     const void* v_for_logits = in_kernel_v ? V : nullptr;
     EaSideStream* side = (use_vnorm && !in_kernel_v) ? ea_side_stream() : nullptr;
     // host threads enqueueing on different streams of one device share the side stream and its two
@@ -959,7 +1450,14 @@ static cudaError_t launch_ea_t(const Dims& d, int dtype, const void* K, const vo
         // group with a head that has no bias and stores nothing (Llama-3.2-3B: 3, Qwen2-7B: 7, Llama-3.1-70B: 8).
         if (d.D != 128 && d.D != 64) return cudaErrorNotSupported;
         const bool d128 = d.D == 128;
-        if (G == 1)
+        if (pair_path) {
+            if (G % 4 == 0)
+                e = d128 ? launch_ea_logits_pair_t<T, 128, 2>(d, K, v_for_logits, mu, cov, n_sink, ws, sc, &n_parts, st)
+                         : launch_ea_logits_pair_t<T, 64, 2>(d, K, v_for_logits, mu, cov, n_sink, ws, sc, &n_parts, st);
+            else
+                e = d128 ? launch_ea_logits_pair_t<T, 128, 1>(d, K, v_for_logits, mu, cov, n_sink, ws, sc, &n_parts, st)
+                         : launch_ea_logits_pair_t<T, 64, 1>(d, K, v_for_logits, mu, cov, n_sink, ws, sc, &n_parts, st);
+        } else if (G == 1)
             e = d128 ? launch_ea_logits_t<T, 128, 1>(d, K, v_for_logits, mu, cov, n_sink, ws, sc, &n_parts, st)
                      : launch_ea_logits_t<T, 64, 1>(d, K, v_for_logits, mu, cov, n_sink, ws, sc, &n_parts, st);
         else if (G == 2 || KVP_EA_RESIDENT_HEADS == 2)
