@@ -43,6 +43,18 @@
 #ifndef KVP_EA_EXP
 #define KVP_EA_EXP 0
 #endif
+// CTA-pair kernel knobs: KVP_EA_LD32 = accumulator read back 32 columns per tcgen05.ld (A/B); KVP_EA_EXP2 = TIMING-ONLY
+// (wrong results): bit 0 = the epilogue reads only the first head of each pair from tensor memory, bit 1 = no logits
+// stores, bit 2 = no accumulator read-back / k-row reads / FMAs at all, bit 3 = no online-softmax exponentials, bit 4 = no bias MMA
+#ifndef KVP_EA_LD32
+#define KVP_EA_LD32 0
+#endif
+#ifndef KVP_EA_EXP2
+#define KVP_EA_EXP2 0
+#endif
+#ifndef KVP_EA_PAIR_BOUNDS
+#define KVP_EA_PAIR_BOUNDS 384   // __launch_bounds__ of the pair kernel (384 threads): up to 168 registers (512 -> 128: +3.6 us, run17)
+#endif
 
 namespace kvp {
 
@@ -50,9 +62,13 @@ namespace kvp {
 __device__ long long g_ea_prof[32];
 #define EA_T0() const long long _t0 = clock64()
 #define EA_ACC(slot) do { if (blockIdx.x == 0) g_ea_prof[slot] += clock64() - _t0; } while (0)
+#define EA_T1() const long long _t1 = clock64()
+#define EA_ACC1(slot) do { if (blockIdx.x == 0) g_ea_prof[slot] += clock64() - _t1; } while (0)
 #else
 #define EA_T0() do {} while (0)
 #define EA_ACC(slot) do {} while (0)
+#define EA_T1() do {} while (0)
+#define EA_ACC1(slot) do {} while (0)
 #endif
 
 constexpr int kEaTile = 128;      // key rows per MMA tile (M)
@@ -602,7 +618,7 @@ __host__ __device__ inline int ea2_pair_of(long long item, long long total, int 
 }
 
 template <typename T, int D, int NH>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(KVP_EA_PAIR_BOUNDS, 1)
 ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapCov,
                       const __grid_constant__ CUtensorMap mapV, const T* __restrict__ mu, int H, int Hq, int S,
                       int n_sink, int R, int n_tiles128, int n_tp, int n_pairs, int n_parts, EaScratch sc, int S_pad,
@@ -638,6 +654,9 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
     const int c = (int)umma::cluster_ctarank();
     const bool leader = c == 0;
     const int P = blockIdx.x >> 1;
+#ifdef KVP_EA_PROFILE
+    const long long t_entry = clock64();
+#endif
 
     if (tid == 0) {
         umma::prefetch_tmap(&mapK);
@@ -762,10 +781,12 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                                 umma::smem_u32(s_cov + (kp * NH + half) * L::kCovHeadPanel) + kk * 32);
                             umma::mma_f16_ss_pair(tmem + buf * kBufCols, da, db, idesc, k > 0);
                         }
+#if !(KVP_EA_EXP2 & 16)
                         umma::mma_f16_ss_pair(tmem + buf * kBufCols,
                                               umma::smem_desc_k16_noswizzle(umma::smem_u32(s_ax)),
                                               umma::smem_desc_k16_noswizzle(umma::smem_u32(s_bx) + (half * D / 8) * 256),
                                               idesc, 1);
+#endif
                         umma::mma_commit_pair(&t_full[buf]);
                     }
                     umma::mma_commit_pair(&k_empty[stage]);
@@ -792,9 +813,10 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                 if (v_active && (tp % n_split) == hp) {
                     // value norms of this CTA's tile: both warpgroups observe every V phase (one V stage), one of them
                     // reads — the warpgroup without an accumulator for this tile (NH = 1), or alternately (NH = 2)
-                    umma::mbar_wait(&v_full[0], v_it & 1);
+                    { EA_T0(); umma::mbar_wait(&v_full[0], v_it & 1); if (warp == 4 && lane == 0) EA_ACC(6); }
                     const bool reader = (NH == 1) ? ((int)(h_it & 1) != wg) : ((int)(v_it & 1) == wg);
                     if (reader) {
+                        EA_T0();
                         float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll
                         for (int c8 = 0; c8 < D / 8; ++c8) {
@@ -810,6 +832,7 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                         __syncwarp();
                         if (lane == 0) umma::mbar_arrive(&v_empty[0]);
                         if (s < S) sc.vnorm[(size_t)row * S_pad + s] = sqrtf(ss0 + ss1);
+                        if (warp == 4 && lane == 0) EA_ACC(10);
                     }
                     ++v_it;
                 }
@@ -830,6 +853,44 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                     for (int q = 0; q < HPH; ++q)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) acc2[q][j] = 0ull;
+#if !(KVP_EA_EXP2 & 4)
+#if KVP_EA_LD32
+                    // 32 accumulator columns per tcgen05.ld (half as many load round trips per row), double-buffered
+                    constexpr int kC32 = D / 32;
+                    constexpr int kSteps = kC32 * HPH;
+                    uint32_t y[2][32];
+                    umma::tmem_ld32(tbase, y[0]);
+#pragma unroll
+                    for (int cc = 0; cc < kC32; ++cc) {
+                        uint64_t k2[16];  // k values of this row for columns [32cc, 32cc+32) as 16 fp32 pairs
+                        {
+                            const int c0 = cc * 32;
+                            const int kpanel = c0 >> 6;
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch) {
+                                const uint4 v = *reinterpret_cast<const uint4*>(
+                                    krow + kpanel * (kEaTile * 128) + umma::sw128_offset(r, ((c0 & 63) >> 3) + ch));
+                                k2[ch * 4] = pack_f32x2(F16Traits<T>::unpack2(v.x));
+                                k2[ch * 4 + 1] = pack_f32x2(F16Traits<T>::unpack2(v.y));
+                                k2[ch * 4 + 2] = pack_f32x2(F16Traits<T>::unpack2(v.z));
+                                k2[ch * 4 + 3] = pack_f32x2(F16Traits<T>::unpack2(v.w));
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < HPH; ++q) {
+                            const int step = cc * HPH + q;
+                            umma::tmem_ld_wait();
+                            if (step + 1 < kSteps) {
+                                const int cn = (step + 1) / HPH, qn = (step + 1) % HPH;
+                                if (!((KVP_EA_EXP2 & 1) && qn == 1)) umma::tmem_ld32(tbase + qn * D + cn * 32, y[(step + 1) & 1]);
+                            }
+                            const uint32_t* yy = y[step & 1];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                acc2[q][j & 3] = fma_f32x2(k2[j], pack_u32x2(yy[2 * j], yy[2 * j + 1]), acc2[q][j & 3]);
+                        }
+                    }
+#else
                     constexpr int kC16 = D / 16;
                     uint32_t y[2][16];
                     umma::tmem_ld16(tbase, y[0]);
@@ -856,7 +917,7 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                             umma::tmem_ld_wait();
                             if (step + 1 < kSteps) {
                                 const int cn = (step + 1) / HPH, qn = (step + 1) % HPH;
-                                umma::tmem_ld16(tbase + qn * D + cn * 16, y[(step + 1) & 1]);
+                                if (!((KVP_EA_EXP2 & 1) && qn == 1)) umma::tmem_ld16(tbase + qn * D + cn * 16, y[(step + 1) & 1]);
                             }
                             const uint32_t* yy = y[step & 1];
 #pragma unroll
@@ -864,6 +925,10 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                                 acc2[q][j & 3] = fma_f32x2(k2[j], pack_u32x2(yy[2 * j], yy[2 * j + 1]), acc2[q][j & 3]);
                         }
                     }
+#endif
+#else
+                    (void)krow;
+#endif
                     float acc[HPH];
 #pragma unroll
                     for (int q = 0; q < HPH; ++q) {
@@ -880,20 +945,32 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                         umma::mbar_arrive_leader(&t_empty[buf]);
                         umma::mbar_arrive(&k_empty[stage]);
                     }
+                    EA_T1();
 #pragma unroll
                     for (int q = 0; q < HPH; ++q) {
                         const int g = half * HPH + q;
                         const float lg = acc[q] * inv_2d;
                         if (valid) {
+#if !(KVP_EA_EXP2 & 2)
                             sc.logits[((size_t)row * g_total + g_off + g) * S_pad + s] = lg;
+#endif
+#if !(KVP_EA_EXP2 & 8)
                             const float m_new = fmaxf(run_m[q], lg);
                             run_z[q] = run_z[q] * __expf(run_m[q] - m_new) + __expf(lg - m_new);
                             run_m[q] = m_new;
+#else
+                            run_m[q] = fmaxf(run_m[q], lg);
+#endif
                         }
                     }
+                    if (warp == 4 && lane == 0) EA_ACC1(11);
                 }
                 __syncwarp();
             }
+#ifdef KVP_EA_PROFILE
+            if (blockIdx.x == 0 && warp == 4 && lane == 0) g_ea_prof[12] += clock64() - t_entry;
+            if (blockIdx.x == 0 && warp == 8 && lane == 0) g_ea_prof[13] += clock64() - t_entry;
+#endif
             // ---- warp-level (max, sum-exp) per head slot -> shared ---------------------------------------------------
 #pragma unroll
             for (int q = 0; q < HPH; ++q) {
@@ -937,6 +1014,10 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
         }
     }
 
+#ifdef KVP_EA_PROFILE
+    if (blockIdx.x == 0 && tid == 0) g_ea_prof[7] += clock64() - t_entry;
+    if (blockIdx.x == 0 && tid == 32) g_ea_prof[14] = i_end - i_begin;
+#endif
     umma::fence_before_sync();
     __syncthreads();
     umma::cluster_sync();  // the peer may still be reading its accumulators / this CTA's barriers

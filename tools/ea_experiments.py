@@ -27,7 +27,7 @@ for vn in (False, True):
     out.append("vnorm=%%d %%.1f" %% (vn, best))
 print("  ".join(out))
 ''' % ROOT
-libs = ["default"] + sorted(f for f in os.listdir(os.path.join(ROOT, "tools", "bin")) if f.startswith("libv_eaexp") or f.startswith("libv_heads"))
+libs = ["default"] + sorted(f for f in os.listdir(os.path.join(ROOT, "tools", "bin")) if f.startswith("libv_"))
 for rnd in range(2):
     for lib in libs:
         env = dict(os.environ)
