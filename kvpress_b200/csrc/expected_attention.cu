@@ -43,12 +43,9 @@
 #ifndef KVP_EA_EXP
 #define KVP_EA_EXP 0
 #endif
-// CTA-pair kernel knobs: KVP_EA_LD32 = accumulator read back 32 columns per tcgen05.ld (A/B); KVP_EA_EXP2 = TIMING-ONLY
+// CTA-pair kernel knob: KVP_EA_EXP2 = TIMING-ONLY
 // (wrong results): bit 0 = the epilogue reads only the first head of each pair from tensor memory, bit 1 = no logits
 // stores, bit 2 = no accumulator read-back / k-row reads / FMAs at all, bit 3 = no online-softmax exponentials, bit 4 = no bias MMA
-#ifndef KVP_EA_LD32
-#define KVP_EA_LD32 0
-#endif
 #ifndef KVP_EA_EXP2
 #define KVP_EA_EXP2 0
 #endif
@@ -854,43 +851,6 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
 #pragma unroll
                         for (int j = 0; j < 4; ++j) acc2[q][j] = 0ull;
 #if !(KVP_EA_EXP2 & 4)
-#if KVP_EA_LD32
-                    // 32 accumulator columns per tcgen05.ld (half as many load round trips per row), double-buffered
-                    constexpr int kC32 = D / 32;
-                    constexpr int kSteps = kC32 * HPH;
-                    uint32_t y[2][32];
-                    umma::tmem_ld32(tbase, y[0]);
-#pragma unroll
-                    for (int cc = 0; cc < kC32; ++cc) {
-                        uint64_t k2[16];  // k values of this row for columns [32cc, 32cc+32) as 16 fp32 pairs
-                        {
-                            const int c0 = cc * 32;
-                            const int kpanel = c0 >> 6;
-#pragma unroll
-                            for (int ch = 0; ch < 4; ++ch) {
-                                const uint4 v = *reinterpret_cast<const uint4*>(
-                                    krow + kpanel * (kEaTile * 128) + umma::sw128_offset(r, ((c0 & 63) >> 3) + ch));
-                                k2[ch * 4] = pack_f32x2(F16Traits<T>::unpack2(v.x));
-                                k2[ch * 4 + 1] = pack_f32x2(F16Traits<T>::unpack2(v.y));
-                                k2[ch * 4 + 2] = pack_f32x2(F16Traits<T>::unpack2(v.z));
-                                k2[ch * 4 + 3] = pack_f32x2(F16Traits<T>::unpack2(v.w));
-                            }
-                        }
-#pragma unroll
-                        for (int q = 0; q < HPH; ++q) {
-                            const int step = cc * HPH + q;
-                            umma::tmem_ld_wait();
-                            if (step + 1 < kSteps) {
-                                const int cn = (step + 1) / HPH, qn = (step + 1) % HPH;
-                                if (!((KVP_EA_EXP2 & 1) && qn == 1)) umma::tmem_ld32(tbase + qn * D + cn * 32, y[(step + 1) & 1]);
-                            }
-                            const uint32_t* yy = y[step & 1];
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                acc2[q][j & 3] = fma_f32x2(k2[j], pack_u32x2(yy[2 * j], yy[2 * j + 1]), acc2[q][j & 3]);
-                        }
-                    }
-#else
                     constexpr int kC16 = D / 16;
                     uint32_t y[2][16];
                     umma::tmem_ld16(tbase, y[0]);
@@ -925,7 +885,6 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                                 acc2[q][j & 3] = fma_f32x2(k2[j], pack_u32x2(yy[2 * j], yy[2 * j + 1]), acc2[q][j & 3]);
                         }
                     }
-#endif
 #else
                     (void)krow;
 #endif

@@ -11,11 +11,16 @@ for w in ${PROFILE_WORKLOADS:-ea_128k knorm_128k snapkv_32k snapkv_128k_70b deco
   echo "$w: $(grep -c -E 'kernel' gpurun_out/r02_launches_${w}.csv) metric rows"
 done
 if [ "${PROFILE_FULL:-1}" = "1" ]; then
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:ea_logits -s 3 -c 1 -f -o gpurun_out/r02_prof_ea_logits \
-      python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-extras --no-graph --workload ea_128k > /dev/null 2>&1
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:select_compact -s 3 -c 1 -f -o gpurun_out/r02_prof_ea_select \
-      python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-extras --no-graph --workload ea_128k > /dev/null 2>&1
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:knorm_cluster -s 3 -c 1 -f -o gpurun_out/r02_prof_knorm_cluster \
-      python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-extras --no-graph --workload decoding_knorm > /dev/null 2>&1
+  NCU="timeout 300 ncu --set full --clock-control none --import-source on -s 3 -c 1 -f"
+  B="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-extras --no-graph"
+  $NCU -k regex:ea_logits_pair -o gpurun_out/r02_prof_ea_logits_pair $B --workload ea_128k > /dev/null 2>&1
+  KVP_EA_PAIR=0 $NCU -k regex:ea_logits_kernel -o gpurun_out/r02_prof_ea_logits_onecta $B --workload ea_128k > /dev/null 2>&1
+  $NCU -k regex:select_compact -o gpurun_out/r02_prof_ea_select $B --workload ea_128k > /dev/null 2>&1
+  $NCU -k regex:ea_finalize -o gpurun_out/r02_prof_ea_finalize $B --workload ea_128k > /dev/null 2>&1
+  $NCU -k regex:knorm_score -o gpurun_out/r02_prof_knorm_score $B --workload knorm_128k > /dev/null 2>&1
+  $NCU -k regex:select_compact -o gpurun_out/r02_prof_knorm_select $B --workload knorm_128k > /dev/null 2>&1
+  $NCU -k regex:snap_stats -o gpurun_out/r02_prof_snap_stats $B --workload snapkv_32k > /dev/null 2>&1
+  $NCU -k regex:snap_colsum -o gpurun_out/r02_prof_snap_colsum $B --workload snapkv_32k > /dev/null 2>&1
+  $NCU -k regex:knorm_cluster -o gpurun_out/r02_prof_knorm_cluster $B --workload decoding_knorm > /dev/null 2>&1
   ls -la gpurun_out/r02_prof_*.ncu-rep
 fi
