@@ -8,6 +8,47 @@ namespace kvp {
 constexpr int kScoreChunk = 256;  // positions per score work item (== kTile)
 static_assert(kScoreChunk == kTile, "score chunks and select tiles share the key layout");
 
+
+// Sum of `v[u]` over the LPR lanes of a row group for the U rows a lane batch covers, WITHOUT reducing every row on
+// every lane: a butterfly that halves the number of live values per step ("transpose-reduce"). Step with lane mask m:
+// a lane keeps the upper half of its values if (sub & m), the lower half otherwise, sends the other half to its
+// partner and adds what it receives. After min(log2 LPR, log2 U) steps a lane holds U / 2^steps totals-so-far; masks
+// that are left reduce plainly. On return slot i of lane `sub` holds the full sum of row `row_of(sub) + i` for
+// i < kSlots, and only lanes with (sub & kIdleMask) == 0 need to finish it: 8 shuffles instead of 32 per 8 rows of
+// head_dim 128, and the sqrt / rounding / key tail runs once per lane batch with every active lane on a different row
+// (the score kernels were co-limited by issue slots: ncu 68 % busy, profiles/r02_prof_knorm_score_details.txt).
+template <int LPR, int U>
+struct RowSums {
+    static constexpr int log2c(int x) { return x <= 1 ? 0 : 1 + log2c(x / 2); }
+    static constexpr int kT = log2c(LPR) < log2c(U) ? log2c(LPR) : log2c(U);  // transpose steps
+    static constexpr int kSlots = U >> kT;                                     // rows a lane ends up with
+    static constexpr int kIdleMask = (LPR >> kT) - 1;                          // lanes with these bits set hold copies
+    __device__ __forceinline__ static int row_of(int sub) {
+        int u = 0;
+#pragma unroll
+        for (int t = 0; t < kT; ++t)
+            if (sub & (LPR >> (t + 1))) u += U >> (t + 1);
+        return u;
+    }
+    __device__ __forceinline__ static void reduce(float (&v)[U], int sub) {
+#pragma unroll
+        for (int t = 0; t < kT; ++t) {
+            const int m = LPR >> (t + 1), half = U >> (t + 1);
+            const bool upper = (sub & m) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const float send = upper ? v[i] : v[i + half];
+                const float keep = upper ? v[i + half] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, m);
+            }
+        }
+#pragma unroll
+        for (int m = (LPR >> kT) / 2; m >= 1; m >>= 1)
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) v[i] += __shfl_xor_sync(0xFFFFFFFFu, v[i], m);
+    }
+};
+
 // Writes -||k_s||_2 (rounded once to the storage dtype) and its ordered key for the 256 positions of
 // `chunk` into shared memory. 256 threads; a sub-warp of LPR lanes per 2*D-byte row, U independent
 // 128-bit loads in flight per lane. Caller synchronises before reading skeys / sscores.
@@ -43,24 +84,28 @@ __device__ __forceinline__ void knorm_score_chunk(const T* __restrict__ K, Strid
             if (s < S && sub < nvec)
                 v[u] = kHint != 0 ? ldg_hint(base + (int64_t)s * ks.s, pol) : ldg_plain(base + (int64_t)s * ks.s);
         }
+        float ssu[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t w[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z,
                                    (uint32_t)v[u].w};
-            float ss = 0.f;
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float2 f = F16Traits<T>::unpack2(w[j]);
-                ss = fmaf(f.x, f.x, ss);
-                ss = fmaf(f.y, f.y, ss);
+                s0 = fmaf(f.x, f.x, s0);
+                s1 = fmaf(f.y, f.y, s1);
             }
+            ssu[u] = s0 + s1;
+        }
+        using RS = RowSums<LPR, U>;
+        RS::reduce(ssu, sub);
+        if ((sub & RS::kIdleMask) == 0) {
 #pragma unroll
-            for (int off = LPR / 2; off >= 1; off >>= 1)
-                ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
-            if (sub == 0) {
-                const int sl = warp * TOK_PER_WARP + (it + u) * RPW + rsel;
+            for (int i = 0; i < RS::kSlots; ++i) {
+                const int sl = warp * TOK_PER_WARP + (it + RS::row_of(sub) + i) * RPW + rsel;
                 // -sqrt(ss) rounded once to the storage dtype (negation is exact)
-                const uint16_t bits = F16Traits<T>::from_float(sqrtf(ss)) ^ 0x8000u;
+                const uint16_t bits = F16Traits<T>::from_float(sqrtf(ssu[i])) ^ 0x8000u;
                 sscores[sl] = bits;
                 skeys[sl] = ordered_key16(bits, F16Traits<T>::kInfBits);
             }
@@ -93,19 +138,25 @@ __device__ __forceinline__ void row_norm_chunk(const T* __restrict__ X, Strides3
             v[u] = make_int4(0, 0, 0, 0);
             if (s < S && sub < nvec) v[u] = ldg_hint(base + (int64_t)s * xs.s, pol);
         }
+        float ssu[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t w[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z, (uint32_t)v[u].w};
-            float ss = 0.f;
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float2 f = F16Traits<T>::unpack2(w[j]);
-                ss = fmaf(f.x, f.x, ss);
-                ss = fmaf(f.y, f.y, ss);
+                s0 = fmaf(f.x, f.x, s0);
+                s1 = fmaf(f.y, f.y, s1);
             }
+            ssu[u] = s0 + s1;
+        }
+        using RS = RowSums<LPR, U>;
+        RS::reduce(ssu, sub);
+        if ((sub & RS::kIdleMask) == 0) {
 #pragma unroll
-            for (int off = LPR / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
-            if (sub == 0) snorm[warp * TOK_PER_WARP + (it + u) * RPW + rsel] = sqrtf(ss);
+            for (int i = 0; i < RS::kSlots; ++i)
+                snorm[warp * TOK_PER_WARP + (it + RS::row_of(sub) + i) * RPW + rsel] = sqrtf(ssu[i]);
         }
     }
 }

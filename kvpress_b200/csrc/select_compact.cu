@@ -175,6 +175,7 @@ struct SelectSmem {
     int list[kTile];
     uint32_t wsum[2][8];
     uint32_t thr[3];
+    uint32_t meta[2];  // compact item: the row's threshold key and tie budget, fetched by the polling thread
     int item;
     int b1;
     int last;
@@ -351,7 +352,11 @@ __device__ __forceinline__ void refine_item(SelectSmem& sm, int row, int group, 
 }
 
 // ---- compact item: (row, tile of kTile == kTileThreads positions, one per thread) ---------------------
-template <typename TR = void>  // TR = void: plain copy; TR = cache dtype: KeyRerotationPress epilogue
+// kKeysReady: the row's keys were complete before this kernel started (two-kernel path): their load is issued BEFORE
+// the wait for the row scan, and the polling thread fetches the row's threshold right behind the flag, so an item is
+// ticket -> (keys || flag + threshold) -> rank -> copy instead of five dependent global round trips (ncu: CTA-barrier
+// waits behind those round trips were the top stall of this kernel, profiles/r02_prof_ea_select_details.txt).
+template <typename TR = void, bool kKeysReady = false>  // TR = void: plain copy; TR = cache dtype: KeyRerotationPress epilogue
 __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, const char* K,
                                              const char* V, Strides3 ks, Strides3 vs, char* K_out,
                                              char* V_out, int32_t* idx_out, int H, int S, int D,
@@ -360,6 +365,8 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = row / H, h = row % H;
     const int s = tile * kTile + tid;
+    uint32_t key = 0;
+    if (kKeysReady) key = __ldcg(&ws.keys[(size_t)row * ws.S_pad + s]);  // in flight during the wait below
     SEL_T0(t_wait);
     // The row scan publishes tile_prefix[row][tile] = {kept_before + 1, tied_before + 1} last (the table is
     // zeroed by the per-call memset), so one polled load doubles as the readiness flag (bounded spin;
@@ -384,13 +391,18 @@ __device__ __forceinline__ void compact_item(SelectSmem& sm, int row, int tile, 
         __threadfence();
         sm.thr[0] = v.x - 1u;
         sm.thr[1] = v.y - 1u;
+        if (!sm.abort) {  // published before the prefix table (scan_row): valid once the flag is up
+            const uint2 m = __ldcg(&ws.row_meta[row]);
+            sm.meta[0] = m.x;
+            sm.meta[1] = m.y;
+        }
     }
     __syncthreads();
     if (sm.abort) return;
     SEL_ACC(0, t_wait);
     SEL_T0(t_rank);
-    const uint32_t key = __ldcg(&ws.keys[(size_t)row * ws.S_pad + s]);
-    const uint2 meta = __ldcg(&ws.row_meta[row]);
+    if (!kKeysReady) key = __ldcg(&ws.keys[(size_t)row * ws.S_pad + s]);
+    const uint2 meta = make_uint2(sm.meta[0], sm.meta[1]);
     const uint2 before = make_uint2(sm.thr[0], sm.thr[1]);
     const uint32_t T = meta.x, n_take = meta.y;
     const uint32_t gt_before = before.x, eq_before = before.y;
@@ -464,14 +476,20 @@ select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, St
     const int nA = R * n_groups, nB = R * ws.n_tiles;
     pdl_wait();  // keys + histograms of the score stage are complete and visible
     SEL_T0(t_kernel);
+    // The ticket of the NEXT item is drawn while the current one is processed (its round trip hides behind the item).
+    // A CTA therefore holds one ticket it has not started; deadlock-free as before: a held refine ticket belongs to a
+    // CTA that is processing an earlier refine item, and refine items never wait.
+    uint32_t next_ticket = 0;
+    if (threadIdx.x == 0) next_ticket = atomicAdd(&ws.counters[0], 1u);
     while (true) {
         SEL_T0(t_ticket);
         __syncthreads();  // previous item's shared state is dead
-        if (threadIdx.x == 0) sm.item = (int)atomicAdd(&ws.counters[0], 1u);
+        if (threadIdx.x == 0) sm.item = (int)next_ticket;
         __syncthreads();
         SEL_ACC(4, t_ticket);
         const int item = sm.item;
         if (item >= nA + nB) break;
+        if (threadIdx.x == 0) next_ticket = atomicAdd(&ws.counters[0], 1u);
         if (item < nA) {
             SEL_T0(t_ref);
             refine_item(sm, item / n_groups, item % n_groups, n_groups, S, n_kept, ws);
@@ -481,7 +499,7 @@ select_compact_kernel(const char* __restrict__ K, const char* __restrict__ V, St
             const int j = item - nA;
             const int row = R - 1 - j / ws.n_tiles;
             const int tile = ws.n_tiles - 1 - j % ws.n_tiles;
-            compact_item<TR>(sm, row, tile, K, V, ks, vs, K_out, V_out, idx_out, H, S, D, n_kept, ws, inv_freq);
+            compact_item<TR, true>(sm, row, tile, K, V, ks, vs, K_out, V_out, idx_out, H, S, D, n_kept, ws, inv_freq);
         }
     }
     SEL_ACC(7, t_kernel);
