@@ -29,8 +29,7 @@
  *   - Selection rule: the n_kept largest scores per (b, h) row; ties at the threshold are
  *     resolved towards the LOWEST position (deterministic; torch.topk leaves it unspecified).
  *   - Caller owns all memory (outputs + workspace of kvp_workspace_bytes()). The library
- *     allocates no device memory and never synchronises the stream (kvp_workspace_check and the *_host
- *     convenience call excepted). Process-wide state is limited to write-once caches of device
+ *     allocates no device memory and never synchronises the stream (kvp_workspace_check excepted). Process-wide state is limited to write-once caches of device
  *     properties (SM count, occupancy, function attributes) and, for ExpectedAttention with
  *     use_vnorm, ONE internal side stream + two events per device: the ||v|| kernel is forked onto it
  *     and joined back into the caller's stream before the call returns; host threads enqueueing
@@ -182,13 +181,9 @@ int kvp_scores_compress_rerotate(const kvp_problem* p, const void* scores, const
                                  void* V_out, int32_t* idx_out, void* workspace,
                                  size_t workspace_bytes, kvp_stream_t stream);
 
-/* ---- host-buffer convenience (end-to-end path): pageable or pinned HOST K/V in, HOST K'/V'
- * out; device staging buffers live in `workspace` (kvp_host_workspace_bytes). Copies are
- * enqueued on `stream`; the call returns after the stream has been synchronised. ---------- */
-int kvp_host_workspace_bytes(const kvp_problem* p, int scorer, size_t* bytes_out);
-int kvp_knorm_compress_host(const kvp_problem* p, const void* K_host, const void* V_host,
-                            void* K_out_host, void* V_out_host, int32_t* idx_out_host,
-                            void* workspace, size_t workspace_bytes, kvp_stream_t stream);
+/* Host buffers: every entry point takes DEVICE pointers (V may be pinned host memory for the scorers that do not read V to
+ * score: the compaction kernel then gathers the kept V rows over PCIe). Staging whole caches from host memory through
+ * these calls — per-kv-head chunks on three streams — is the host side's job: kvpress_b200/host_staging.py. */
 
 #ifdef __cplusplus
 }

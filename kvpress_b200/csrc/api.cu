@@ -469,71 +469,4 @@ int kvp_scores_compress_rerotate(const kvp_problem* p, const void* scores, const
     return e == cudaSuccess ? KVP_OK : fail_cuda(e);
 }
 
-// ---- host-buffer end-to-end path -------------------------------------------------------------------
-// workspace = [K_dev | V_dev | K_out_dev | V_out_dev | idx_dev | kernel scratch]
-static void host_layout(const Dims& d, size_t* k_off, size_t* v_off, size_t* ko_off,
-                        size_t* vo_off, size_t* idx_off, size_t* ws_off) {
-    const size_t in_bytes = (size_t)d.R * d.S * d.D * 2;
-    const size_t out_bytes = (size_t)d.R * d.n_kept * d.D * 2;
-    size_t off = 0;
-    *k_off = off; off = align_up(off + in_bytes, 256);
-    *v_off = off; off = align_up(off + in_bytes, 256);
-    *ko_off = off; off = align_up(off + out_bytes, 256);
-    *vo_off = off; off = align_up(off + out_bytes, 256);
-    *idx_off = off; off = align_up(off + (size_t)d.R * d.n_kept * 4, 256);
-    *ws_off = off;
-}
-
-int kvp_host_workspace_bytes(const kvp_problem* p, int scorer, size_t* bytes_out) {
-    Dims d;
-    int rc = validate(p, &d, false);
-    if (rc) return rc;
-    if (!bytes_out) return KVP_ERR_NULL_POINTER;
-    size_t a, b, c, e, f, g;
-    host_layout(d, &a, &b, &c, &e, &f, &g);
-    *bytes_out = g + layout(d, scorer, 256).total;
-    return KVP_OK;
-}
-
-int kvp_knorm_compress_host(const kvp_problem* p, const void* K_host, const void* V_host,
-                            void* K_out_host, void* V_out_host, int32_t* idx_out_host,
-                            void* workspace, size_t workspace_bytes, kvp_stream_t stream) {
-    Dims d;
-    int rc = validate(p, &d, false);
-    if (rc) return rc;
-    if (!K_host || !V_host || !K_out_host || !V_out_host || !workspace)
-        return KVP_ERR_NULL_POINTER;
-    size_t k_off, v_off, ko_off, vo_off, idx_off, ws_off;
-    host_layout(d, &k_off, &v_off, &ko_off, &vo_off, &idx_off, &ws_off);
-    const size_t need = ws_off + layout(d, KVP_SCORER_KNORM, 0).total;
-    if (workspace_bytes < need) return KVP_ERR_WORKSPACE_TOO_SMALL;
-    char* base = static_cast<char*>(workspace);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t in_bytes = (size_t)d.R * d.S * d.D * 2;
-    const size_t out_bytes = (size_t)d.R * d.n_kept * d.D * 2;
-    cudaError_t e;
-    if ((e = cudaMemcpyAsync(base + k_off, K_host, in_bytes, cudaMemcpyHostToDevice, st)))
-        return fail_cuda(e);
-    if ((e = cudaMemcpyAsync(base + v_off, V_host, in_bytes, cudaMemcpyHostToDevice, st)))
-        return fail_cuda(e);
-    kvp_problem q = *p;  // the staged copies are contiguous
-    q.k_stride[0] = q.v_stride[0] = (int64_t)d.H * d.S * d.D;
-    q.k_stride[1] = q.v_stride[1] = (int64_t)d.S * d.D;
-    q.k_stride[2] = q.v_stride[2] = d.D;
-    rc = kvp_knorm_compress(&q, base + k_off, base + v_off, base + ko_off, base + vo_off,
-                            reinterpret_cast<int32_t*>(base + idx_off), nullptr, base + ws_off,
-                            workspace_bytes - ws_off, stream);
-    if (rc) return rc;
-    if ((e = cudaMemcpyAsync(K_out_host, base + ko_off, out_bytes, cudaMemcpyDeviceToHost, st)))
-        return fail_cuda(e);
-    if ((e = cudaMemcpyAsync(V_out_host, base + vo_off, out_bytes, cudaMemcpyDeviceToHost, st)))
-        return fail_cuda(e);
-    if (idx_out_host &&
-        (e = cudaMemcpyAsync(idx_out_host, base + idx_off, (size_t)d.R * d.n_kept * 4,
-                             cudaMemcpyDeviceToHost, st)))
-        return fail_cuda(e);
-    if ((e = cudaStreamSynchronize(st))) return fail_cuda(e);
-    return KVP_OK;
-}
-
 }  // extern "C"

@@ -71,8 +71,6 @@ SIGNATURES = {
     "kvp_scores_select": (ctypes.c_int, [_PP, _P, ctypes.POINTER(ctypes.c_int64), _P, _P, _SZ, _P]),
     "kvp_scores_compress_rerotate": (
         ctypes.c_int, [_PP, _P, ctypes.POINTER(ctypes.c_int64), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
-    "kvp_host_workspace_bytes": (ctypes.c_int, [_PP, ctypes.c_int, ctypes.POINTER(_SZ)]),
-    "kvp_knorm_compress_host": (ctypes.c_int, [_PP, _P, _P, _P, _P, _P, _P, _SZ, _P]),
 }
 
 _lib: Optional[ctypes.CDLL] = None
@@ -594,34 +592,3 @@ def scores_compress_rerotate(scores: torch.Tensor, keys, values, n_kept: int, in
                 "kvp_scores_compress_rerotate",
             )
     return k_out, v_out, idx
-
-
-# --------------------------------------------------------------------------------------------------
-# host-buffer end-to-end path (bench.py `e2e`)
-# --------------------------------------------------------------------------------------------------
-def knorm_compress_host(keys_host: torch.Tensor, values_host: torch.Tensor, n_kept: int, device, workspace=None,
-                        out=None):
-    """K, V are contiguous HOST tensors (ideally pinned); K', V' come back as host tensors."""
-    if keys_host.is_cuda or values_host.is_cuda or not keys_host.is_contiguous() or not values_host.is_contiguous():
-        raise RuntimeError("knorm_compress_host takes contiguous host tensors")
-    B, H, S, D = keys_host.shape
-    p = KvpProblem()
-    p.B, p.Hkv, p.Hq, p.S, p.D, p.n_kept, p.dtype = B, H, H, S, D, int(n_kept), _DTYPES[keys_host.dtype]
-    lib = load()
-    need = _SZ(0)
-    _check(lib.kvp_host_workspace_bytes(ctypes.byref(p), SCORER_KNORM, ctypes.byref(need)), "kvp_host_workspace_bytes")
-    with torch.cuda.device(device):
-        if workspace is None or workspace.numel() < need.value:
-            workspace = torch.empty(need.value, dtype=torch.uint8, device=device)
-        if out is None:
-            k_out = torch.empty((B, H, n_kept, D), dtype=keys_host.dtype).pin_memory()
-            v_out = torch.empty_like(k_out).pin_memory()
-        else:
-            k_out, v_out = out
-        _check(
-            lib.kvp_knorm_compress_host(
-                ctypes.byref(p), _ptr(keys_host), _ptr(values_host), _ptr(k_out), _ptr(v_out), None, _ptr(workspace),
-                workspace.numel(), _stream()),
-            "kvp_knorm_compress_host",
-        )
-    return k_out, v_out, workspace

@@ -15,6 +15,9 @@ from tests.conftest import ulp16_diff
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
+# Distance of the kernels' scores (fp32 math, ONE rounding) to the reference's own 16-bit scores (rounded at ~7 points):
+# asserted bound = the maximum MEASURED over every golden case on the B200 (printed by the tests) + 1.
+REF_ULP_BOUND = 8
 
 
 def _native():
@@ -254,7 +257,9 @@ def _assert_scores_close(got, ref16, hi32, forced: slice, dtype):
     rel = (g.float() - h).abs() / h.abs().clamp_min(1e-30)
     assert rel.max() <= 2.0 ** -8 + 1e-3  # half an ulp of the final rounding + 1e-3 of fp32 math
     d_ref = ulp16_diff(g, r)
-    assert d_ref.max() <= 8 and (d_ref > 2).float().mean() < 2e-2, (int(d_ref.max()), float((d_ref > 2).float().mean()))
+    print(f"[measured] vs reference 16-bit scores: max ulp {int(d_ref.max())}, frac > 2 ulp {float((d_ref > 2).float().mean()):.2e}, "
+          f"exact {float((d_ref == 0).float().mean()):.3f}")
+    assert d_ref.max() <= REF_ULP_BOUND and (d_ref > 2).float().mean() < 2e-2, (int(d_ref.max()), float((d_ref > 2).float().mean()))
     # the forced positions carry the reference's sentinel: round(max + 1)
     sentinel = (g.float().max() + 1).to(dtype)
     assert (got[..., forced] == sentinel).all()
@@ -297,7 +302,7 @@ def test_expected_attention_compress_vs_golden(golden):
         idx_c = idx.cpu()
         assert torch.equal(idx_c.long(), O.select_lowest_index_ties(scores.cpu(), n_kept))
         assert (idx_c[..., :min(4, n_kept)] == torch.arange(min(4, n_kept))).all()  # sinks are kept
-        res = O.check_selection(ref_scores, idx_c, n_kept, ulp_slack=8)
+        res = O.check_selection(ref_scores, idx_c, n_kept, ulp_slack=REF_ULP_BOUND)
         assert res["ok"], res
         assert _jaccard(idx_c, golden.t(f"ea_kept_{i}"), golden.S) > 0.85  # the reference's own 16-bit noise moves a few ranks
 
@@ -351,7 +356,7 @@ def test_snapkv_compress_vs_golden(golden):
         # the observation window is always kept (lowest positions first when n_kept < w)
         if n_kept >= w:
             assert (idx_c[..., -w:] == torch.arange(golden.S - w, golden.S)).all()
-        res = O.check_selection(ref_scores, idx_c, n_kept, ulp_slack=8)
+        res = O.check_selection(ref_scores, idx_c, n_kept, ulp_slack=REF_ULP_BOUND)
         assert res["ok"], res
         if n_kept > 2 * w:  # below that the kept set is (mostly) the window, i.e. ties among sentinels
             # random K/Q give nearly flat attention, so the reference's own 16-bit rounding noise
@@ -711,7 +716,7 @@ def test_keydiff_vs_golden():
             assert torch.equal(sc2, sc)
             assert torch.equal(idx.long().cpu(), O.select_lowest_index_ties(sc.cpu(), n_kept))
             _check_compaction(keys, values, k2, v2, idx)
-            assert O.check_selection(ref, idx.long().cpu(), n_kept, ulp_slack=8)["ok"]
+            assert O.check_selection(ref, idx.long().cpu(), n_kept, ulp_slack=REF_ULP_BOUND)["ok"]
 
 
 @pytest.mark.parametrize("shape", [(1, 8, 32768, 128), (2, 3, 5000, 64), (1, 2, 1023, 256), (3, 1, 257, 32)])
