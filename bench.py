@@ -751,8 +751,8 @@ def main():
     p = native.make_problem(sets[0][0], sets[0][1], n_kept, w["Hq"])
     if w["scorer"] == "knorm_rerotate":  # kvp_knorm_score (1) + kvp_scores_compress_rerotate (generic: 3)
         launches = 1 + native.launches_per_compress(p, 0)
-    elif w["scorer"] == "adakv_ea":  # EA score (memset, logits, vnorm, finalize, sentinel) + 2 x kvp_scores_select (3 each)
-        launches = 5 + 2 * native.launches_per_compress(p, 0)
+    elif w["scorer"] == "adakv_ea":  # EA score (memset, logits incl. value norms, finalize, sentinel) + 2 x kvp_scores_select (3 each)
+        launches = 4 + 2 * native.launches_per_compress(p, 0)
     else:
         scorer_id = {"knorm": 1, "streaming": 2, "snapkv": 3, "expected_attention": 4, "keydiff": 5}[w["scorer"]]
         launches = native.launches_per_compress(p, scorer_id)

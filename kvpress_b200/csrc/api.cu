@@ -181,9 +181,10 @@ int kvp_launches_per_compress(const kvp_problem* p, int scorer, int* launches_ou
         case KVP_SCORER_KEYDIFF: *launches_out = 5; break;  // memset, anchor partials, merge, score, select+compact
         case KVP_SCORER_SNAPKV: *launches_out = 6; break;  // memset, stats, memset, colsum, finalize, select+compact
         case KVP_SCORER_EXPECTED_ATTENTION: {
-            // memset, logits, vnorm (side stream), finalize, select+compact (use_covariance + use_vnorm, the press
-            // defaults; the KVP_EA_TRI experiment adds one)
-            *launches_out = 5;
+            // press defaults (use_covariance + use_vnorm): memset, logits (the tensor-core kernels stage the V tiles and
+            // take the value norms themselves), finalize, select+compact; head dims outside 64 / 128 have no covariance
+            // path here, and the covariance-free scan adds the value-norm kernel on the side stream
+            *launches_out = (p->D == 64 || p->D == 128) ? 4 : 5;
             break;
         }
         default: return KVP_ERR_BAD_ARGUMENT;
