@@ -3,8 +3,8 @@ the CPU oracle and the golden vectors of the imported reference. Needs a B200: `
 
 Bars (north_star): Knorm / StreamingLLM — identical retained-index sets (tie-aware where the
 reference's own top-k is ambiguous, see oracle.check_selection); attention-based scorers — scores
-within 1e-3 relative of the fp32 evaluation of the reference formula, and within 16-bit rounding
-noise (<= 4 ulp, 99.9% <= 2 ulp) of the reference's own 16-bit scores.
+within 1e-3 relative of the fp32 evaluation of the reference formula (<= 1 ulp of the 16-bit score), and within the
+reference's own 16-bit rounding noise of ITS scores: measured <= 2 ulp on every golden case, asserted <= REF_ULP_BOUND = 3.
 """
 import pytest
 import torch
@@ -17,7 +17,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 # Distance of the kernels' scores (fp32 math, ONE rounding) to the reference's own 16-bit scores (rounded at ~7 points):
 # asserted bound = the maximum MEASURED over every golden case on the B200 (printed by the tests) + 1.
-REF_ULP_BOUND = 8
+REF_ULP_BOUND = 3  # measured maximum over all golden cases, round 2: 2 (profiles/r02_gpu_tests_final.txt)
+# tie band of the kept-set validity check against the REFERENCE's scores: a kept position may sit one score distance
+# below the kernel's threshold, which itself may sit one score distance below the reference's
+SEL_ULP_SLACK = 2 * REF_ULP_BOUND
 
 
 def _native():
@@ -302,7 +305,7 @@ def test_expected_attention_compress_vs_golden(golden):
         idx_c = idx.cpu()
         assert torch.equal(idx_c.long(), O.select_lowest_index_ties(scores.cpu(), n_kept))
         assert (idx_c[..., :min(4, n_kept)] == torch.arange(min(4, n_kept))).all()  # sinks are kept
-        res = O.check_selection(ref_scores, idx_c, n_kept, ulp_slack=REF_ULP_BOUND)
+        res = O.check_selection(ref_scores, idx_c, n_kept, ulp_slack=SEL_ULP_SLACK)
         assert res["ok"], res
         assert _jaccard(idx_c, golden.t(f"ea_kept_{i}"), golden.S) > 0.85  # the reference's own 16-bit noise moves a few ranks
 
@@ -356,7 +359,7 @@ def test_snapkv_compress_vs_golden(golden):
         # the observation window is always kept (lowest positions first when n_kept < w)
         if n_kept >= w:
             assert (idx_c[..., -w:] == torch.arange(golden.S - w, golden.S)).all()
-        res = O.check_selection(ref_scores, idx_c, n_kept, ulp_slack=REF_ULP_BOUND)
+        res = O.check_selection(ref_scores, idx_c, n_kept, ulp_slack=SEL_ULP_SLACK)
         assert res["ok"], res
         if n_kept > 2 * w:  # below that the kept set is (mostly) the window, i.e. ties among sentinels
             # random K/Q give nearly flat attention, so the reference's own 16-bit rounding noise
@@ -684,7 +687,7 @@ def test_adakv_selection_at_128k():
 # ---------------------------------------------------------------------------------------------------
 def _assert_keydiff_scores(got: torch.Tensor, keys_cpu: torch.Tensor, ref16=None):
     """Kernel score == fp32 evaluation of the reference formula rounded once (<= 1 ulp; absolute 2^-9 around the
-    sign change where ulps shrink to nothing); within 8 ulp of the reference's own 16-bit scores."""
+    sign change where ulps shrink to nothing); within REF_ULP_BOUND ulp of the reference's own 16-bit scores."""
     got = got.cpu()
     hi = O.keydiff_scores_fp32(keys_cpu)
     want = hi.to(got.dtype)
@@ -716,7 +719,7 @@ def test_keydiff_vs_golden():
             assert torch.equal(sc2, sc)
             assert torch.equal(idx.long().cpu(), O.select_lowest_index_ties(sc.cpu(), n_kept))
             _check_compaction(keys, values, k2, v2, idx)
-            assert O.check_selection(ref, idx.long().cpu(), n_kept, ulp_slack=REF_ULP_BOUND)["ok"]
+            assert O.check_selection(ref, idx.long().cpu(), n_kept, ulp_slack=8)["ok"]  # KeyDiff: <= 8 ulp asserted above
 
 
 @pytest.mark.parametrize("shape", [(1, 8, 32768, 128), (2, 3, 5000, 64), (1, 2, 1023, 256), (3, 1, 257, 32)])

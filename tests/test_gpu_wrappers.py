@@ -101,7 +101,7 @@ def test_large32k_scores_and_kept_sets_vs_reference(large, record_property):
     scored = {"knorm": slice(0, S), "snap": slice(0, S - w), "ea": slice(4, S), "tova": slice(0, S - 1)}
     # measured bounds (asserted with a small margin): Knorm <= 1 ulp (fp32 summation order); the attention scorers
     # sit within the reference's own rounding noise (it rounds to bf16 at ~7 points, the kernels once)
-    bound = {"knorm": (1, 0.0), "snap": (8, 2e-2), "ea": (8, 2e-2), "tova": (8, 2e-2)}
+    bound = {"knorm": (1, 0.0), "snap": (2, 0.0), "ea": (3, 0.0), "tova": (3, 0.0)}   # measured: 0 / 1 / 2 / 2 ulp, none > 2
     for tag, sc in got.items():
         ref = large.t(f"{tag}_scores")
         rep = _report(tag, sc.cpu(), ref, scored[tag])
@@ -113,7 +113,7 @@ def test_large32k_scores_and_kept_sets_vs_reference(large, record_property):
             idx = nat.scores_select(sc, n_kept).cpu()
             ref_kept = large.t(f"{tag}_kept_{i}")
             # tie-aware validity against the REFERENCE's scores, slack = the measured score noise
-            res = O.check_selection(ref, idx, n_kept, ulp_slack=bound[tag][0])
+            res = O.check_selection(ref, idx, n_kept, ulp_slack=2 * bound[tag][0])  # score distance of the position + of the threshold
             # membership flips: (a) against the reference's own kept set — dominated by how torch.topk happened to
             # break the ties at the threshold score (bf16 scores of a 32k row take few distinct values); (b) strict:
             # kept positions scoring BELOW / dropped positions scoring ABOVE the reference's threshold (no tie band),
