@@ -4,8 +4,20 @@ the CPU oracle and the golden vectors of the imported reference. Needs a B200: `
 Bars (north_star): Knorm / StreamingLLM — identical retained-index sets (tie-aware where the
 reference's own top-k is ambiguous, see oracle.check_selection); attention-based scorers — scores
 within 1e-3 relative of the fp32 evaluation of the reference formula (<= 1 ulp of the 16-bit score), and within the
-reference's own 16-bit rounding noise of ITS scores: measured <= 2 ulp on every stored golden case and <= 4 ulp against the
-oracle evaluated on the box's host, asserted <= # Asserted distance = the MEASURED maximum of round 2 + 1 (profiles/r02_gpu_tests_final.txt):
+reference's own 16-bit rounding noise of ITS scores: measured <= 2 ulp on every stored golden case (asserted <= 3) and <= 4 ulp
+against the oracle evaluated on the box's host, whose bf16 GEMMs vary with the host CPU (asserted <= 8, < 2 % beyond 2 ulp).
+"""
+import pytest
+import torch
+
+from oracle import press_oracle as O
+from tests.conftest import ulp16_diff
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+# Distance of the kernels' scores (fp32 math, ONE rounding) to the reference's own 16-bit scores (rounded at ~7 points).
+# Asserted = the MEASURED maximum of round 2 + 1 (profiles/r02_gpu_tests_final.txt, DESIGN.md 5.4):
 #  * against the STORED goldens (outputs of the imported reference, fixed): measured <= 2 ulp, none beyond 2 -> 3;
 #  * against the oracle evaluated on the box's host at test time: the oracle's bf16 CPU GEMMs round differently from host to
 #    host (tests/conftest.py), measured 4 ulp with 1.4e-4 of the positions beyond 2 -> the round-1 band of 8 / 2 % is kept.
