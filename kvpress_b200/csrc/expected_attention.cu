@@ -614,6 +614,21 @@ __host__ __device__ inline int ea2_pair_of(long long item, long long total, int 
     return p;
 }
 
+// Host-callable view of the partition for the CPU test of the schedule (tests/test_abi_symbols.py): for `pair` of
+// `n_pairs` over `n_units` units of `n_tp` items: out4 = {first item, one past the last item}; for `unit`:
+// {first pair that touches it, number of pairs that touch it}. Returns -1 on bad arguments.
+extern "C" int kvp_debug_ea_pair_partition(int n_units, int n_tp, int n_pairs, int pair, int unit, long long* out4) {
+    if (n_units < 1 || n_tp < 1 || n_pairs < 1 || out4 == nullptr) return -1;
+    const long long total = (long long)n_units * n_tp;
+    if ((long long)n_pairs > total || pair < 0 || pair >= n_pairs || unit < 0 || unit >= n_units) return -1;
+    out4[0] = ea2_start(pair, total, n_pairs);
+    out4[1] = ea2_start(pair + 1, total, n_pairs);
+    const int first = ea2_pair_of((long long)unit * n_tp, total, n_pairs);
+    out4[2] = first;
+    out4[3] = ea2_pair_of((long long)(unit + 1) * n_tp - 1, total, n_pairs) - first + 1;
+    return 0;
+}
+
 template <typename T, int D, int NH>
 __global__ void __launch_bounds__(KVP_EA_PAIR_BOUNDS, 1)
 ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapCov,

@@ -173,3 +173,41 @@ def test_fused_knorm_queue_is_a_valid_schedule():
             if lag == 1 and r + 1 < R:  # the head of the next row's score items sits in front of the first compact item
                 head = min(m_head, nT)
                 assert all(pos[(0, r + 1, i)] < first_compact for i in range(head))
+
+
+def test_ea_pair_kernel_partition_is_balanced_and_complete():
+    """Work partition of the CTA-pair ExpectedAttention kernel (expected_attention.cu: ea2_start / ea2_pair_of): the
+    (unit, tile-pair) items are cut into contiguous ranges, one per CTA pair. Every item belongs to exactly one pair,
+    range sizes differ by at most one item, and for every unit the pairs that touch it are exactly
+    [first, first + count) — the slots of the per-CTA softmax partials the kernel writes (two per pair) and the
+    finalize kernel merges; slots beyond 2 * count are neutralised by the unit's first CTA."""
+    import ctypes
+
+    from kvpress_b200 import native
+
+    lib = ctypes.CDLL(str(native.library_path()))
+    fn = lib.kvp_debug_ea_pair_partition
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_longlong)]
+    out = (ctypes.c_longlong * 4)()
+    for n_units, n_tp, n_pairs in [(16, 512, 74), (8, 512, 74), (1, 1024, 74), (4, 10, 40), (4, 10, 3), (3, 7, 21),
+                                   (2, 1, 2), (1, 1, 1), (16, 512, 73), (5, 13, 64), (80, 512, 72)]:
+        total = n_units * n_tp
+        owner = [-1] * total
+        sizes = []
+        for p in range(n_pairs):
+            assert fn(n_units, n_tp, n_pairs, p, 0, out) == 0
+            lo, hi = out[0], out[1]
+            assert 0 <= lo < hi <= total, (n_units, n_tp, n_pairs, p, lo, hi)   # n_pairs <= total: no empty range
+            sizes.append(hi - lo)
+            for i in range(lo, hi):
+                assert owner[i] == -1
+                owner[i] = p
+        assert all(o >= 0 for o in owner) and max(sizes) - min(sizes) <= 1
+        for u in range(n_units):
+            assert fn(n_units, n_tp, n_pairs, 0, u, out) == 0
+            first, count = out[2], out[3]
+            touching = sorted(set(owner[u * n_tp:(u + 1) * n_tp]))
+            assert touching == list(range(first, first + count)), (n_units, n_tp, n_pairs, u)
+            assert 2 * count <= 160                                            # kEaMaxParts slots per (row, head)
+    assert fn(4, 10, 41, 0, 0, out) == -1                                      # more pairs than items: the launcher clamps
