@@ -30,8 +30,9 @@
  *     resolved towards the LOWEST position (deterministic; torch.topk leaves it unspecified).
  *   - Caller owns all memory (outputs + workspace of kvp_workspace_bytes()). The library
  *     allocates no device memory and never synchronises the stream (kvp_workspace_check excepted). Process-wide state is limited to write-once caches of device
- *     properties (SM count, occupancy, function attributes) and, for ExpectedAttention with
- *     use_vnorm, ONE internal side stream + two events per device: the ||v|| kernel is forked onto it
+ *     properties (SM count, occupancy, function attributes) and, for the covariance-free ExpectedAttention
+ *     scan with use_vnorm (the tensor-core kernels take the value norms themselves), ONE internal side
+ *     stream + two events per device: the ||v|| kernel is forked onto it
  *     and joined back into the caller's stream before the call returns; host threads enqueueing
  *     ExpectedAttention calls on the same device serialise on a mutex for those few microseconds.
  *     Calls are re-entrant per (stream, workspace); every call is CUDA-graph capturable.
