@@ -574,7 +574,7 @@ ea_logits_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
 //
 // Work: unit = (row, group of 2*NH heads); item = (unit, pair of consecutive 128-position tiles). The items are cut
 // into equal contiguous ranges, one per CTA pair (any number of pairs; a range may cross a unit boundary). CTA `c` of
-// the pair owns tile 2*tp + c of item tp: stages it (TMA, completion counted on the LEADER's barrier), holds
+// the pair owns tile 2*tp + c of item tp: stages it (TMA on its own barrier; a forwarding thread tells the leader), holds
 // the covariance of head 2*half + c of each half, reads its 128 x N accumulator rows from its own tensor memory and
 // finishes them exactly like the one-CTA kernel. Only the leader issues MMAs; its commits arrive on the barriers of
 // both CTAs; the peer's epilogue releases accumulator buffers on the leader's barrier.
@@ -646,7 +646,7 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
     unsigned char* s_bx = smem + L::kBxOff;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
     constexpr int kStages = L::kStages;
-    uint64_t* k_full = bars;          // [kStages]  used in the leader only: both CTAs' tiles have landed
+    uint64_t* k_full = bars;          // [kStages]  per CTA: THIS CTA's tile has landed (its epilogue reads the k rows)
     uint64_t* k_empty = bars + 4;     // [kStages]  per CTA: MMA commit + the warps that read this CTA's k rows
     uint64_t* t_full = bars + 8;      // [2]        per CTA: MMA commit (multicast)
     uint64_t* t_empty = bars + 10;    // [2]        used in the leader only: 4 warps of each CTA drained the buffer
@@ -655,6 +655,7 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
     uint64_t* v_full = bars + 14;     // [1]        per CTA
     uint64_t* v_empty = bars + 16;    // [1]        per CTA
     float* s_red = reinterpret_cast<float*>(bars + 18);  // [8 warps][2 head slots][2]
+    uint64_t* k_pair = bars + 40;     // [kStages]  used in the leader only: one arrival per CTA = both tiles have landed
 
     constexpr int HPH = 2;            // heads per half: head 2*half + c lives in CTA c
     constexpr int kN = HPH * D;       // MMA N (both CTAs together)
@@ -677,6 +678,7 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
         for (int i = 0; i < kStages; ++i) {
             umma::mbar_init(&k_full[i], 1);
             umma::mbar_init(&k_empty[i], 1 + 4 * NH);  // MMA commit + the epilogue warps that read the tile's k rows
+            umma::mbar_init(&k_pair[i], 2);            // the forwarding thread of each CTA
         }
         for (int i = 0; i < 2; ++i) {
             umma::mbar_init(&t_full[i], 1);
@@ -751,10 +753,21 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                 for (int tp = tp_begin; tp < tp_end; ++tp, ++k_it) {
                     const int stage = k_it % kStages;
                     { EA_T0(); umma::mbar_wait(&k_empty[stage], ((k_it / kStages) & 1) ^ 1); EA_ACC(0); }
-                    if (leader) umma::mbar_arrive_expect_tx(&k_full[stage], 2 * L::kStageBytes);
+                    umma::mbar_arrive_expect_tx(&k_full[stage], L::kStageBytes);
                     for (int kp = 0; kp < L::kPanels; ++kp)
-                        umma::tma_load_4d_pair(s_stage + stage * L::kStageBytes + kp * (kEaTile * 128), &mapK,
-                                               &k_full[stage], kp * 64, (2 * tp + c) * kEaTile, h, b);
+                        umma::tma_load_4d(s_stage + stage * L::kStageBytes + kp * (kEaTile * 128), &mapK,
+                                          &k_full[stage], kp * 64, (2 * tp + c) * kEaTile, h, b);
+                }
+            }
+        } else if (warp == 2) {
+            // ===== forwarder (both CTAs): "my K tile has landed" -> the leader's pair barrier. Each CTA's tile completes
+            // on its OWN barrier, so its epilogue (generic-proxy reads of the k rows) observes the completion itself; the
+            // MMA issuer waits for one arrival per CTA (release at cluster scope -> its acquire) =====
+            if (lane == 0) {
+                for (int tp = tp_begin; tp < tp_end; ++tp, ++k_it) {
+                    const int stage = k_it % kStages;
+                    umma::mbar_wait(&k_full[stage], (k_it / kStages) & 1);
+                    umma::mbar_arrive_leader(&k_pair[stage]);
                 }
             }
         } else if (warp == 3) {
@@ -777,7 +790,7 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                 umma::mbar_wait(cov_full, cov_it & 1);
                 for (int tp = tp_begin; tp < tp_end; ++tp, ++k_it) {
                     const int stage = k_it % kStages;
-                    { EA_T0(); umma::mbar_wait(&k_full[stage], (k_it / kStages) & 1); EA_ACC(1); }
+                    { EA_T0(); umma::mbar_wait(&k_pair[stage], (k_it / kStages) & 1); EA_ACC(1); }
                     umma::fence_after_sync();
                     const uint32_t a_base = umma::smem_u32(s_stage + stage * L::kStageBytes);
 #pragma unroll 1
@@ -852,9 +865,10 @@ ea_logits_pair_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                 for (int half = 0; half < NH; ++half, ++h_it) {
                     const int buf = h_it & 1;
                     if (buf != wg) continue;
+                    umma::mbar_wait(&k_full[stage], (k_it / kStages) & 1);  // this CTA's k rows are visible to these threads
                     {
                         EA_T0();
-                        umma::mbar_wait(&t_full[buf], (h_it >> 1) & 1);  // implies: both K tiles landed and were consumed
+                        umma::mbar_wait(&t_full[buf], (h_it >> 1) & 1);
                         if (warp == 4 && lane == 0) EA_ACC(4);
                     }
                     EA_T0();

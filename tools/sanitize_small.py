@@ -21,6 +21,10 @@ outs.append(native.streaming_compress(k, v, n_kept, 4, return_indices=True))
 outs.append(native.snapkv_compress(k, v, q, w, 5, n_kept, return_indices=True, return_scores=True))
 outs.append(native.expected_attention_compress(k, v, mu, cov, 0.0, 4, True, n_kept, return_indices=True, return_scores=True))
 outs.append(native.expected_attention_compress(k, v, mu, None, 0.0, 4, True, n_kept, return_indices=True))
+# group sizes 2 (CTA-pair kernel, one half per tile) and 3 (one-CTA kernel with a padding head)
+for hq in (4, 6):
+    outs.append(native.expected_attention_compress(k, v, mu[:, :hq].contiguous(), cov[:, :hq].contiguous(), 0.0, 4, True, n_kept,
+                                                   return_indices=True))
 sc = torch.randn(B, H, S, device=dev).to(torch.bfloat16)
 outs.append(native.scores_compress(sc, k, v, n_kept, return_indices=True))
 torch.cuda.synchronize()
